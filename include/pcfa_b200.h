@@ -1,0 +1,280 @@
+/*
+ * pcfa_b200.h — C ABI of libpcfa_b200.so, the B200 (sm_100a) implementation of the
+ * cost-volume / warping / objective operators on PCFA's optimisation hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C, raw DEVICE pointers, int sizes, `stream` is a cudaStream_t passed as void*;
+ *   - tensors are dense, contiguous, fp32, NCHW unless stated; index arithmetic is int32/int64;
+ *   - asynchronous and stream-ordered: no allocation, no host synchronisation, re-entrant;
+ *   - return 0 on success, a positive cudaError_t value if a CUDA call/launch failed, or a
+ *     negative PCFA_E_* code for argument errors.  Nothing throws.
+ *   - outputs documented "(overwritten)" need no initialisation; "(accumulated)" are += targets.
+ *
+ * Every function cites the reference interface it replaces (paths relative to the
+ * cv-stuttgart/PCFA checkout).  The reference binds these through pybind11 modules taking
+ * at::Tensor; the stub a maintainer would add on the reference side is in INTEGRATION.md.
+ */
+#ifndef PCFA_B200_H
+#define PCFA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCFA_ABI_VERSION 1
+
+#define PCFA_OK            0
+#define PCFA_E_BADARG     -1   /* null pointer / non-positive size / unsupported parameter */
+#define PCFA_E_TOOLARGE   -2   /* a dimension exceeds what the int32 index maps support     */
+#define PCFA_E_NODEVICE   -3   /* no sm_100 device / driver entry point unavailable         */
+#define PCFA_E_WORKSPACE  -4   /* workspace pointer null or too small                       */
+
+typedef void* pcfa_stream_t;
+
+/* ---- library info -------------------------------------------------------------------- */
+int         pcfa_abi_version(void);
+/* Human-readable text for a status returned by any entry point (static storage). */
+const char* pcfa_status_string(int status);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t     pcfa_launch_count(void);
+
+/* ======================================================================================
+ * (a1) All-pairs correlation pyramid — replaces CorrBlock.__init__ + CorrBlock.corr
+ *      models/raft/corr.py:13-27,52-60 ; models/gma/corr.py:16-30,55-63
+ *
+ *   level0[b*N+i, y, x] = (1/sqrt(C)) * sum_c fmap1[b,c,i] * fmap2[b,c,y*W+x],  N = H*W
+ *   level(l+1) = avg_pool2d(level l, 2, stride 2)   (floor sizes: H_{l+1} = H_l/2)
+ *
+ * The pyramid lives in ONE flat fp32 buffer; level l starts at offsets[l] floats and is a dense
+ * [B*N, H_l, W_l] array.  pcfa_corr_pyramid_layout fills offsets/hs/ws (host arrays of
+ * num_levels entries, offsets has num_levels+1: the last one is the total float count).
+ * ====================================================================================== */
+int pcfa_corr_pyramid_layout(int B, int H, int W, int num_levels,
+                             int64_t* offsets, int* hs, int* ws);
+
+/* Bytes of scratch needed by pcfa_corr_pyramid_forward / _backward for these sizes. */
+int64_t pcfa_corr_pyramid_workspace_bytes(int B, int C, int H, int W, int num_levels);
+
+/* impl: 0 = auto (tcgen05 path when C % 64 == 0, otherwise SIMT), 1 = force SIMT fp32,
+ *       2 = force tcgen05 (bf16x3 split, fp32 accumulate in TMEM). */
+int pcfa_corr_pyramid_forward(const float* fmap1, const float* fmap2,
+                              float* pyramid /* (overwritten) */,
+                              void* workspace, int64_t workspace_bytes,
+                              int B, int C, int H, int W, int num_levels, int impl,
+                              pcfa_stream_t stream);
+
+/* Backward of the build (autograd of matmul + avg_pool2d in the reference, corr.py:25-27,58-60).
+ * grad_pyramid has the pyramid's flat layout and holds dL/d(level l) for every level.
+ *   grad_fmap1[b,c,i] = (1/sqrt C) sum_l sum_j g_l[b*N+i, j] * pool_l(fmap2)[b,c,j]
+ *   grad_fmap2        = (1/sqrt C) sum_l unpool_l( g_l^T * fmap1 )
+ * grad_fmap1 / grad_fmap2 are overwritten. */
+int pcfa_corr_pyramid_backward(const float* grad_pyramid,
+                               const float* fmap1, const float* fmap2,
+                               float* grad_fmap1, float* grad_fmap2,
+                               void* workspace, int64_t workspace_bytes,
+                               int B, int C, int H, int W, int num_levels, int impl,
+                               pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a2/a3) Multi-level bilinear lookup — replaces CorrBlock.__call__ → bilinear_sampler →
+ *      F.grid_sample(align_corners=True, zeros)   models/raft/corr.py:29-50,
+ *      models/raft/utils/utils.py:57-71 (same in models/gma/corr.py:32-53)
+ *
+ *   coords [B,2,H,W] (channel 0 = x, 1 = y, level-0 pixel units)
+ *   out    [B, num_levels*(2r+1)^2, H, W],  channel = l*(2r+1)^2 + a*(2r+1) + b,
+ *          sample position (x/2^l + a - r, y/2^l + b - r)   — a moves x (x-major window).
+ * Backward scatters into grad_pyramid (accumulated; flat pyramid layout); coords get no
+ * gradient (detached in the reference, models/raft/raft.py:123).
+ * ====================================================================================== */
+int pcfa_corr_lookup_forward(const float* pyramid, const float* coords,
+                             float* out /* (overwritten) */,
+                             int B, int H, int W, int num_levels, int radius,
+                             pcfa_stream_t stream);
+
+int pcfa_corr_lookup_backward(const float* grad_out, const float* coords,
+                              float* grad_pyramid /* (accumulated) */,
+                              int B, int H, int W, int num_levels, int radius,
+                              pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a5) Spatial correlation sampler — replaces spatial_correlation_sampler_backend.forward /
+ *      .backward  (Correlation_Module/correlation_sampler.cpp:58-117, CPU semantics of
+ *      Correlation_Module/correlation.cpp:75-178).  PWCNet call: models/PWCNet/PWCNet.py:45-58.
+ *
+ *   out[n,ph,pw,h,w] = sum_c sum_{i<kH} sum_{j<kW} in1[n,c,i1,j1] * in2[n,c,i2,j2]
+ *   i1 = -padH + h*dH + i*dilH, i2 = i1 + (ph - (patchH-1)/2)*dilPatchH  (same for j / W);
+ *   terms with any index out of range are skipped.  out is [B,patchH,patchW,oH,oW] with
+ *   oH = (iH + 2*padH - ((kH-1)*dilH+1))/dH + 1.   `scale` multiplies the result (1.0 for the
+ *   sampler itself; PWCNet's "/C" may be folded in by the caller).
+ * ====================================================================================== */
+typedef struct pcfa_scs_params {
+    int kH, kW, patchH, patchW, padH, padW, dilH, dilW, dilPatchH, dilPatchW, dH, dW;
+} pcfa_scs_params;
+
+int pcfa_scs_output_size(int iH, int iW, const pcfa_scs_params* p, int* oH, int* oW);
+
+int pcfa_scs_forward(const float* in1, const float* in2, float* out /* (overwritten) */,
+                     int B, int C, int iH, int iW, const pcfa_scs_params* p, float scale,
+                     pcfa_stream_t stream);
+
+int pcfa_scs_backward(const float* in1, const float* in2, const float* grad_out,
+                      float* grad_in1, float* grad_in2 /* (both overwritten) */,
+                      int B, int C, int iH, int iW, const pcfa_scs_params* p, float scale,
+                      pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a7) FlowNet2 correlation — replaces correlation_cuda.forward / .backward
+ *      models/FlowNet/correlation_package/correlation_cuda.cc:10-87,89-171 and the kernels in
+ *      correlation_cuda_kernel.cu:46-334.  The padded NHWC copies rbot1/rbot2 of the reference are
+ *      not materialised (zero padding is a predicate).  corr_multiply is accepted and ignored, as
+ *      in the reference.  Output [B, D*D, oH, oW], D = 2*(max_disp/stride2)+1, already divided by
+ *      kernel_size^2 * C.  Backward follows the reference's truncating integer division
+ *      (correlation_cuda_kernel.cu:172-176,290-294).
+ * ====================================================================================== */
+int pcfa_fn2corr_output_size(int H, int W, int pad_size, int kernel_size, int max_disp,
+                             int stride1, int stride2, int* outC, int* oH, int* oW);
+
+int pcfa_fn2corr_forward(const float* in1, const float* in2, float* out /* (overwritten) */,
+                         int B, int C, int H, int W,
+                         int pad_size, int kernel_size, int max_disp, int stride1, int stride2,
+                         pcfa_stream_t stream);
+
+int pcfa_fn2corr_backward(const float* in1, const float* in2, const float* grad_out,
+                          float* grad_in1, float* grad_in2 /* (both overwritten) */,
+                          int B, int C, int H, int W,
+                          int pad_size, int kernel_size, int max_disp, int stride1, int stride2,
+                          pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a8) Resample2d — replaces resample2d_cuda.forward / .backward
+ *      models/FlowNet/resample2d_package/resample2d_cuda.cc:6-31, resample2d_kernel.cu:15-198.
+ *   img [B,C,H,W], flow [B,2,oH,oW] → out [B,C,oH,oW]; border-clamped bilinear (or nearest when
+ *   bilinear == 0).  Only kernel_size == 1 is supported (the only value the reference uses,
+ *   models/FlowNet/FlowNet2.py:39-80).  Backward reproduces the reference's quirks: image weights
+ *   use xf - trunc(xf) (kernel.cu:105-106), flow gradient uses floor (kernel.cu:163-193).
+ * ====================================================================================== */
+int pcfa_resample2d_forward(const float* img, const float* flow, float* out /* (overwritten) */,
+                            int B, int C, int H, int W, int oH, int oW,
+                            int kernel_size, int bilinear, pcfa_stream_t stream);
+
+int pcfa_resample2d_backward(const float* img, const float* flow, const float* grad_out,
+                             float* grad_img  /* (accumulated; caller zero-fills like resample2d.py:38) */,
+                             float* grad_flow /* (overwritten) */,
+                             int B, int C, int H, int W, int oH, int oW,
+                             int kernel_size, int bilinear, pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a9) ChannelNorm — replaces channelnorm_cuda.forward / .backward
+ *      models/FlowNet/channelnorm_package/channelnorm_cuda.cc:6-30, channelnorm_kernel.cu:18-96.
+ *   out[b,0,y,x] = sqrt(sum_c x^2);  gin = gout * x / (out + 1e-9).  norm_deg is ignored (L2).
+ * ====================================================================================== */
+int pcfa_channelnorm_forward(const float* x, float* out, int B, int C, int H, int W,
+                             int norm_deg, pcfa_stream_t stream);
+int pcfa_channelnorm_backward(const float* x, const float* out, const float* grad_out,
+                              float* grad_x /* (overwritten) */, int B, int C, int H, int W,
+                              int norm_deg, pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a6) PWCNet backward warp — replaces PWCDCNet.warp (models/PWCNet/PWCNet.py:166-206):
+ *   two F.grid_sample calls (bilinear, zeros, align_corners=False on an align_corners=True-style
+ *   normalisation) and the >= 1e-4 validity mask, fused.
+ *   x [B,C,H,W], flow [B,2,H,W] → out [B,C,H,W].  Backward gives d/dx (accumulated, caller
+ *   zero-fills) and d/dflow (overwritten); the mask carries no gradient.
+ * ====================================================================================== */
+int pcfa_pwc_warp_forward(const float* x, const float* flow, float* out,
+                          int B, int C, int H, int W, pcfa_stream_t stream);
+int pcfa_pwc_warp_backward(const float* x, const float* flow, const float* grad_out,
+                           float* grad_x, float* grad_flow,
+                           int B, int C, int H, int W, pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a10) Box constraint / input transform — replaces ScaledInputModel.forward's pre-processing
+ *      (helper_functions/own_models.py:62-85) fused with extract_deltas / extract_deltas_joint
+ *      (attack_PCFA.py:20-37).
+ *
+ *   mode PCFA_BOX_COV      : var = w (per image);   x = clamp(0.5*(tanh(w)+(1-eps))/(1-eps),0,1)
+ *                            delta = 0.5*(tanh(w)+(1-eps))/(1-eps) - image
+ *   mode PCFA_BOX_CLIP     : var = image+delta;     x = clamp(var,0,1);  delta = x - image
+ *   mode PCFA_BOX_JOINT    : var = delta (shared);  x = clamp(image+delta,0,1);
+ *                            delta' = clamp(clamp(delta+other_max,0,1)-other_max+other_min,0,1)-other_min
+ *                            (penalty sees delta'; `aux_max`/`aux_min` = max/min(image1,image2))
+ *   mode PCFA_BOX_UNIVERSAL: var = delta [1,C,H,W] broadcast over the batch; x = clamp(image+delta,0,1);
+ *                            penalty sees the raw delta.
+ *   net_in = scale * x  (scale = 255 for RAFT/GMA/FlowNet2, 1 for PWCNet/SpyNet).
+ *   sumsq_partials[PCFA_BOX_PARTIALS] receives deterministic per-block partial sums of delta^2
+ *   (sum them in index order; pcfa_objective_loss does).
+ * ====================================================================================== */
+#define PCFA_BOX_COV        0
+#define PCFA_BOX_CLIP       1
+#define PCFA_BOX_JOINT      2
+#define PCFA_BOX_UNIVERSAL  3
+#define PCFA_BOX_PARTIALS   1024
+
+int pcfa_box_forward(const float* var, const float* image,
+                     const float* aux_max, const float* aux_min,   /* JOINT only, else NULL */
+                     float* net_in /* (overwritten) [B,C,H,W] */,
+                     float* delta_out /* optional (may be NULL) */,
+                     float* sumsq_partials /* (overwritten) [PCFA_BOX_PARTIALS] */,
+                     int mode, int B, int64_t chw, float eps_box, float scale,
+                     pcfa_stream_t stream);
+
+/* dL/dvar (overwritten; for UNIVERSAL summed over the batch) from dL/dnet_in and the penalty:
+ *   penalty_coef = mu * 2 / numel_total if the penalty is active else 0, read from
+ *   loss_terms[2] (device; written by pcfa_objective_loss) so no host sync is needed. */
+int pcfa_box_backward(const float* var, const float* image,
+                      const float* aux_max, const float* aux_min,
+                      const float* grad_net_in /* may be NULL: penalty only */,
+                      const float* loss_terms,
+                      float* grad_var /* overwritten, or accumulated when accumulate != 0 (second
+                                         image of a shared perturbation) */,
+                      int accumulate,
+                      int mode, int B, int64_t chw, float eps_box, float scale,
+                      pcfa_stream_t stream);
+
+
+/* d delta/d var applied to an arbitrary gradient (autograd of extract_deltas / extract_deltas_joint,
+ * attack_PCFA.py:20-37, when the deltas feed something other than the fused loss).  UNIVERSAL: identity. */
+int pcfa_box_delta_backward(const float* var, const float* aux_max, const float* aux_min,
+                            const float* grad_delta, float* grad_var, int accumulate,
+                            int mode, int64_t numel, float eps_box, pcfa_stream_t stream);
+
+/* Deterministic partial sums of x^2 (PCFA_BOX_PARTIALS floats) — two_norm_avg_delta_squared's
+ * reduction (helper_functions/losses.py:110-126) for deltas that did not come from pcfa_box_forward. */
+int pcfa_sumsq_partials(const float* x, int64_t numel, float* sumsq_partials, pcfa_stream_t stream);
+
+/* ======================================================================================
+ * (a11/a12) Loss + penalty — replaces losses.loss_delta_constraint (helper_functions/losses.py:
+ *      200-230) with avg_epe :3-30 / avg_mse :32-44 / f_cosim :76-88 (including its operator-
+ *      precedence quirk), relu_penalty :177-197, and InputPadder.unpad (ownutilities.py:51-62)
+ *      without the .cpu() round trip of postprocess_flow (ownutilities.py:297).
+ *
+ *   flow [B,2,Hp,Wp] is the PADDED network output; target [B,2,H,W] is unpadded; the crop is
+ *   rows [pad_top, pad_top+H), cols [pad_left, pad_left+W).
+ *   loss_terms (device, 4 floats, overwritten):
+ *     [0] = loss = sim + mu*max(0, sumsq/numel - bound^2), [1] = sim, [2] = penalty_coef
+ *     (mu*2/numel if active else 0), [3] = sumsq/numel.
+ *   grad_flow [B,2,Hp,Wp] (overwritten; zero in the padding) = d sim / d flow.
+ *   sumsq_partials: one or two arrays of PCFA_BOX_PARTIALS floats (second may be NULL);
+ *   numel_total = numel(delta1)+numel(delta2) as in losses.py:122-126.
+ * ====================================================================================== */
+#define PCFA_LOSS_AEE   0
+#define PCFA_LOSS_MSE   1
+#define PCFA_LOSS_COSIM 2
+
+int pcfa_objective_loss(const float* flow, const float* target,
+                        const float* sumsq_partials1, const float* sumsq_partials2,
+                        float sumsq_weight1, float sumsq_weight2,
+                        float* loss_terms, float* grad_flow /* may be NULL */,
+                        void* workspace /* >= pcfa_objective_workspace_bytes() */,
+                        int loss_type, int B, int H, int W, int Hp, int Wp,
+                        int pad_top, int pad_left,
+                        double numel_total, float delta_bound, float mu,
+                        pcfa_stream_t stream);
+int64_t pcfa_objective_workspace_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCFA_B200_H */

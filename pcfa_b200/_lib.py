@@ -1,0 +1,112 @@
+"""ctypes binding of libpcfa_b200.so — the only bridge between the PyTorch host code and the CUDA
+kernels.  Signatures mirror include/pcfa_b200.h one to one.  There is no CPU fallback: if the
+library is missing or a tensor is not a CUDA tensor the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpcfa_b200.so"
+_lib = None
+
+c_fp = C.c_void_p      # device pointers travel as void*
+c_i = C.c_int
+c_i64 = C.c_int64
+c_f = C.c_float
+c_d = C.c_double
+
+
+class ScsParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("kH", "kW", "patchH", "patchW", "padH", "padW", "dilH", "dilW",
+                                       "dilPatchH", "dilPatchW", "dH", "dW")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pcfa_b200.h
+SIGNATURES = {
+    "pcfa_abi_version": (c_i, []),
+    "pcfa_status_string": (C.c_char_p, [c_i]),
+    "pcfa_launch_count": (c_i64, []),
+    "pcfa_corr_pyramid_layout": (c_i, [c_i, c_i, c_i, c_i, C.POINTER(c_i64), C.POINTER(c_i), C.POINTER(c_i)]),
+    "pcfa_corr_pyramid_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i, c_i]),
+    "pcfa_corr_pyramid_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_pyramid_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_lookup_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_lookup_backward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_scs_output_size": (c_i, [c_i, c_i, C.POINTER(ScsParams), C.POINTER(c_i), C.POINTER(c_i)]),
+    "pcfa_scs_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),
+    "pcfa_scs_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),
+    "pcfa_fn2corr_output_size": (c_i, [c_i, c_i, c_i, c_i, c_i, c_i, c_i, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i)]),
+    "pcfa_fn2corr_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_fn2corr_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_resample2d_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_resample2d_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_channelnorm_forward": (c_i, [c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_channelnorm_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_pwc_warp_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_pwc_warp_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_box_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i64, c_f, c_f, c_fp]),
+    "pcfa_box_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i64, c_f, c_f, c_fp]),
+    "pcfa_box_delta_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i64, c_f, c_fp]),
+    "pcfa_sumsq_partials": (c_i, [c_fp, c_i64, c_fp, c_fp]),
+    "pcfa_objective_loss": (c_i, [c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i,
+                                  c_i, c_i, c_i, c_i, c_d, c_f, c_f, c_fp]),
+    "pcfa_objective_workspace_bytes": (c_i64, []),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and attach argtypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing — build it with `python -m pcfa_b200._build` "
+            "(or __graft_entry__.build()).  pcfa_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pcfa_abi_version() != 1:
+        raise RuntimeError("libpcfa_b200.so ABI version mismatch — rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().pcfa_status_string(status).decode()
+        raise RuntimeError(f"{what or 'pcfa_b200'} failed with status {status}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None → NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors, name="pcfa_b200 operator"):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"{name}: expected CUDA tensors (pcfa_b200 has no CPU path), got {t.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name}: expected float32 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name}: expected contiguous tensors")
+
+
+def launch_count() -> int:
+    return int(load().pcfa_launch_count())

@@ -1,0 +1,338 @@
+"""RAFT (Teed & Deng, ECCV 2020) around the B200 CorrBlock.
+
+Architecturally identical to the network the reference vendors (models/raft/raft.py:24-144,
+update.py, extractor.py) and state-dict compatible with its checkpoints (`module.`-prefixed keys of
+the DataParallel wrapper are accepted, ownutilities.py:105-107), so a user can load
+`raft-sintel.pth` unchanged.  Only the cost-volume operator differs: `corr_block` is injected
+(default: pcfa_b200.corr_block.CorrBlock) — tests inject the oracle to obtain reference flows.
+
+Convolutions, norms and the GRU stay in cuDNN/ATen (library code, not on this project's kernel
+list).  Dead work of the reference's test-mode forward is not executed: the convex-upsampling
+mask head and `upsample_flow` run only for the last iteration, because `test_mode=True` returns
+nothing else (raft.py:141-142) — outputs and gradients are unchanged.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _norm(kind: str, ch: int) -> nn.Module:
+    if kind == "group":
+        return nn.GroupNorm(num_groups=ch // 8, num_channels=ch)
+    if kind == "batch":
+        return nn.BatchNorm2d(ch)
+    if kind == "instance":
+        return nn.InstanceNorm2d(ch)
+    if kind == "none":
+        return nn.Sequential()
+    raise ValueError(kind)
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, cin, cout, norm_fn="group", stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1 = _norm(norm_fn, cout)
+        self.norm2 = _norm(norm_fn, cout)
+        self.downsample = None
+        if stride != 1:
+            self.norm3 = _norm(norm_fn, cout)       # registered twice (norm3 / downsample.1) like the reference
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return self.relu(x + y)
+
+
+class BottleneckBlock(nn.Module):
+    def __init__(self, cin, cout, norm_fn="group", stride=1):
+        super().__init__()
+        q = cout // 4
+        self.conv1 = nn.Conv2d(cin, q, 1)
+        self.conv2 = nn.Conv2d(q, q, 3, padding=1, stride=stride)
+        self.conv3 = nn.Conv2d(q, cout, 1)
+        self.relu = nn.ReLU(inplace=True)
+        if norm_fn == "group":
+            g = cout // 8
+            self.norm1, self.norm2 = nn.GroupNorm(g, q), nn.GroupNorm(g, q)
+            self.norm3 = nn.GroupNorm(g, cout)
+        else:
+            self.norm1, self.norm2, self.norm3 = _norm(norm_fn, q), _norm(norm_fn, q), _norm(norm_fn, cout)
+        self.downsample = None
+        if stride != 1:
+            self.norm4 = nn.GroupNorm(cout // 8, cout) if norm_fn == "group" else _norm(norm_fn, cout)
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm4)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        y = self.relu(self.norm3(self.conv3(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return self.relu(x + y)
+
+
+def _init_encoder(mod: nn.Module):
+    for m in mod.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)):
+            if m.weight is not None:
+                nn.init.constant_(m.weight, 1)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class _Encoder(nn.Module):
+    """Shared trunk logic of BasicEncoder / SmallEncoder: stem, three stages, 1x1 head."""
+    block = ResidualBlock
+    widths = (64, 64, 96, 128)
+
+    def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0):
+        super().__init__()
+        self.norm_fn = norm_fn
+        stem, w1, w2, w3 = self.widths
+        self.norm1 = nn.GroupNorm(8, stem) if norm_fn == "group" else _norm(norm_fn, stem)
+        self.conv1 = nn.Conv2d(3, stem, 7, stride=2, padding=3)
+        self.relu1 = nn.ReLU(inplace=True)
+        self.in_planes = stem
+        self.layer1 = self._stage(w1, 1)
+        self.layer2 = self._stage(w2, 2)
+        self.layer3 = self._stage(w3, 2)
+        self.conv2 = nn.Conv2d(w3, output_dim, 1)
+        self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
+        _init_encoder(self)
+
+    def _stage(self, dim, stride):
+        blocks = nn.Sequential(self.block(self.in_planes, dim, self.norm_fn, stride=stride),
+                               self.block(dim, dim, self.norm_fn, stride=1))
+        self.in_planes = dim
+        return blocks
+
+    def forward(self, x):
+        pair = isinstance(x, (tuple, list))
+        if pair:
+            nb = x[0].shape[0]
+            x = torch.cat(x, dim=0)
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return torch.split(x, [nb, nb], dim=0) if pair else x
+
+
+class BasicEncoder(_Encoder):
+    block = ResidualBlock
+    widths = (64, 64, 96, 128)
+
+
+class SmallEncoder(_Encoder):
+    block = BottleneckBlock
+    widths = (32, 32, 64, 96)
+
+
+class FlowHead(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, 2, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+def _gru_step(h, x, cz, cr, cq):
+    hx = torch.cat([h, x], dim=1)
+    z = torch.sigmoid(cz(hx))
+    r = torch.sigmoid(cr(hx))
+    q = torch.tanh(cq(torch.cat([r * h, x], dim=1)))
+    return (1 - z) * h + z * q
+
+
+class ConvGRU(nn.Module):
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        c = hidden_dim + input_dim
+        self.convz = nn.Conv2d(c, hidden_dim, 3, padding=1)
+        self.convr = nn.Conv2d(c, hidden_dim, 3, padding=1)
+        self.convq = nn.Conv2d(c, hidden_dim, 3, padding=1)
+
+    def forward(self, h, x):
+        return _gru_step(h, x, self.convz, self.convr, self.convq)
+
+
+class SepConvGRU(nn.Module):
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        c = hidden_dim + input_dim
+        for tag, k, p in (("1", (1, 5), (0, 2)), ("2", (5, 1), (2, 0))):
+            for gate in "zrq":
+                setattr(self, f"conv{gate}{tag}", nn.Conv2d(c, hidden_dim, k, padding=p))
+
+    def forward(self, h, x):
+        h = _gru_step(h, x, self.convz1, self.convr1, self.convq1)      # horizontal
+        return _gru_step(h, x, self.convz2, self.convr2, self.convq2)   # vertical
+
+
+class BasicMotionEncoder(nn.Module):
+    def __init__(self, corr_levels, corr_radius):
+        super().__init__()
+        cor_planes = corr_levels * (2 * corr_radius + 1) ** 2
+        self.convc1 = nn.Conv2d(cor_planes, 256, 1)
+        self.convc2 = nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1 = nn.Conv2d(2, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        return torch.cat([out, flow], dim=1)
+
+
+class SmallMotionEncoder(nn.Module):
+    def __init__(self, corr_levels, corr_radius):
+        super().__init__()
+        cor_planes = corr_levels * (2 * corr_radius + 1) ** 2
+        self.convc1 = nn.Conv2d(cor_planes, 96, 1)
+        self.convf1 = nn.Conv2d(2, 64, 7, padding=3)
+        self.convf2 = nn.Conv2d(64, 32, 3, padding=1)
+        self.conv = nn.Conv2d(128, 80, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc1(corr))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        return torch.cat([out, flow], dim=1)
+
+
+class BasicUpdateBlock(nn.Module):
+    def __init__(self, corr_levels, corr_radius, hidden_dim=128):
+        super().__init__()
+        self.encoder = BasicMotionEncoder(corr_levels, corr_radius)
+        self.gru = SepConvGRU(hidden_dim=hidden_dim, input_dim=128 + hidden_dim)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=256)
+        self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(256, 64 * 9, 1))
+
+    def forward(self, net, inp, corr, flow, want_mask=True):
+        motion = self.encoder(flow, corr)
+        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        delta_flow = self.flow_head(net)
+        mask = 0.25 * self.mask(net) if want_mask else None     # .25 "to balance gradients" (update.py:135)
+        return net, mask, delta_flow
+
+
+class SmallUpdateBlock(nn.Module):
+    def __init__(self, corr_levels, corr_radius, hidden_dim=96):
+        super().__init__()
+        self.encoder = SmallMotionEncoder(corr_levels, corr_radius)
+        self.gru = ConvGRU(hidden_dim=hidden_dim, input_dim=82 + 64)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=128)
+
+    def forward(self, net, inp, corr, flow, want_mask=True):
+        motion = self.encoder(flow, corr)
+        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        return net, None, self.flow_head(net)
+
+
+def coords_grid(batch, ht, wd, device):
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+def upflow8(flow, mode="bilinear"):
+    new_size = (8 * flow.shape[2], 8 * flow.shape[3])
+    return 8 * F.interpolate(flow, size=new_size, mode=mode, align_corners=True)
+
+
+def convex_upsample(flow, mask):
+    """[N,2,H,W] → [N,2,8H,8W] by a learned convex combination of the 3x3 neighbourhood (raft.py:72-83)."""
+    N, _, H, W = flow.shape
+    mask = torch.softmax(mask.view(N, 1, 9, 8, 8, H, W), dim=2)
+    up = F.unfold(8 * flow, [3, 3], padding=1).view(N, 2, 9, 1, 1, H, W)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 2, 8 * H, 8 * W)
+
+
+DEFAULT_CONFIG = {"small": False, "mixed_precision": False, "epsilon": 1e-8}
+
+
+class RAFT(nn.Module):
+    def __init__(self, args=None, corr_block=None):
+        super().__init__()
+        args = dict(DEFAULT_CONFIG if args is None else (vars(args) if not isinstance(args, dict) else args))
+        self.args = args
+        small = bool(args.get("small", False))
+        if small:
+            self.hidden_dim, self.context_dim = 96, 64
+            args["corr_levels"], args["corr_radius"] = 4, 3
+        else:
+            self.hidden_dim, self.context_dim = 128, 128
+            args["corr_levels"], args["corr_radius"] = 4, 4
+        args.setdefault("dropout", 0)
+        args.setdefault("mixed_precision", False)
+        hd, cd = self.hidden_dim, self.context_dim
+        if small:
+            self.fnet = SmallEncoder(output_dim=128, norm_fn="instance", dropout=args["dropout"])
+            self.cnet = SmallEncoder(output_dim=hd + cd, norm_fn="none", dropout=args["dropout"])
+            self.update_block = SmallUpdateBlock(4, 3, hidden_dim=hd)
+        else:
+            self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", dropout=args["dropout"])
+            self.cnet = BasicEncoder(output_dim=hd + cd, norm_fn="batch", dropout=args["dropout"])
+            self.update_block = BasicUpdateBlock(4, 4, hidden_dim=hd)
+        if corr_block is None:
+            from ..corr_block import CorrBlock as corr_block
+        self.corr_block = corr_block
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        dev_type = image1.device.type
+        # torch.cuda.amp.autocast of the reference is a no-op off-GPU (raft.py:12)
+        amp = bool(self.args["mixed_precision"]) and dev_type == "cuda"
+        with torch.autocast(dev_type, enabled=amp):
+            fmap1, fmap2 = self.fnet([image1, image2])
+        corr_fn = self.corr_block(fmap1.float(), fmap2.float(), radius=self.args["corr_radius"])
+        with torch.autocast(dev_type, enabled=amp):
+            net, inp = torch.split(self.cnet(image1), [self.hidden_dim, self.context_dim], dim=1)
+            net, inp = torch.tanh(net), torch.relu(inp)
+        N, _, H, W = image1.shape
+        coords0 = coords_grid(N, H // 8, W // 8, image1.device)
+        coords1 = coords0.clone()
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        predictions = []
+        flow_up = None
+        for itr in range(iters):
+            coords1 = coords1.detach()
+            corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            need_up = (not test_mode) or itr == iters - 1
+            with torch.autocast(dev_type, enabled=amp):
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
+            coords1 = coords1 + delta_flow
+            if need_up:
+                flow_up = upflow8(coords1 - coords0) if up_mask is None else convex_upsample(coords1 - coords0, up_mask)
+                predictions.append(flow_up)
+        if test_mode:
+            return coords1 - coords0, flow_up
+        return predictions
