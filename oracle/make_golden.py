@@ -1,0 +1,218 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE CODE (imported in place from
+/root/reference, CPU, torch 2.11) on small seeded inputs.  TEST INFRASTRUCTURE ONLY.
+
+Run from the repo root in the authoring container:   python -m oracle.make_golden
+The fixtures are committed; the GPU box never needs /root/reference.
+
+Import shims: stub `mlflow` / `matplotlib` (absent), `np.float = float`
+(ownutilities.py:518), `torch.Tensor.cuda` → identity for PWCNet.warp (PWCNet.py:194), and the
+reference's SCS CPU extension from oracle/_ref on sys.path as `spatial_correlation_sampler_backend`.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference")
+OUT = REPO / "tests" / "golden"
+
+
+def _shim_reference():
+    sys.dont_write_bytecode = True
+    np.float = float
+    ml = types.ModuleType("mlflow")
+    for n in ("log_metric", "log_param", "log_artifacts", "log_artifact", "set_tracking_uri"):
+        setattr(ml, n, lambda *a, **k: None)
+    ml.exceptions = types.SimpleNamespace(MlflowException=Exception)
+    sys.modules["mlflow"] = ml
+    mp = types.ModuleType("matplotlib")
+    mp.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mp, mp.pyplot
+    from oracle import build_ref
+    build_ref.build()
+    assert build_ref.load() is not None, "reference SCS extension failed to build"
+    scs_py = REF / "models/PWCNet/cpu_spatial_correlation_sampler-0.3.0/Correlation_Module"
+    sys.path[:0] = [str(scs_py), str(REF)]
+    os.chdir(REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def golden_corrblock():
+    from models.raft.corr import CorrBlock
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 1, 24, 16, 24
+    f1 = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    f2 = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    base = torch.stack([xs, ys], 0).float()[None].repeat(B, 1, 1, 1)
+    coords_a = base + 3.0 * torch.randn(B, 2, H, W, generator=g)
+    coords_b = base + 12.0 * torch.randn(B, 2, H, W, generator=g)      # many taps out of range
+    coords_b[0, :, 0, 0] = torch.tensor([-50.0, 400.0])
+    coords_b[0, :, 0, 1] = torch.tensor([float(W - 1), float(H - 1)])  # exactly on the last cell
+    coords_b[0, :, 0, 2] = torch.tensor([0.0, 0.0])
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    out_a, out_b = blk(coords_a), blk(coords_b)
+    go_a = torch.randn(out_a.shape, generator=g)
+    go_b = torch.randn(out_b.shape, generator=g)
+    (out_a * go_a).sum().backward(retain_graph=True)
+    g1_a, g2_a = f1.grad.clone(), f2.grad.clone()
+    (out_b * go_b).sum().backward()
+    g1_ab, g2_ab = f1.grad.clone(), f2.grad.clone()                    # two lookups accumulated
+    np.savez_compressed(OUT / "corrblock.npz", fmap1=_np(f1), fmap2=_np(f2), coords_a=_np(coords_a),
+                        coords_b=_np(coords_b), out_a=_np(out_a), out_b=_np(out_b), gout_a=_np(go_a),
+                        gout_b=_np(go_b), g1_a=_np(g1_a), g2_a=_np(g2_a), g1_ab=_np(g1_ab), g2_ab=_np(g2_ab),
+                        level1=_np(blk.corr_pyramid[1]), level2=_np(blk.corr_pyramid[2]),
+                        level3=_np(blk.corr_pyramid[3]), level0_rows=_np(blk.corr_pyramid[0][::37]))
+
+
+def golden_scs():
+    from spatial_correlation_sampler import spatial_correlation_sample
+    g = torch.Generator().manual_seed(12)
+    cases = {"pwc": dict(shape=(2, 6, 9, 11), kw=dict(kernel_size=1, patch_size=9, stride=1)),
+             "fn2like": dict(shape=(1, 5, 10, 13), kw=dict(kernel_size=1, patch_size=7, stride=1, dilation_patch=2)),
+             "general": dict(shape=(1, 4, 11, 12), kw=dict(kernel_size=3, patch_size=5, stride=2, padding=1,
+                                                           dilation=1, dilation_patch=2)),
+             "dilated": dict(shape=(1, 3, 12, 12), kw=dict(kernel_size=(3, 2), patch_size=(3, 5), stride=(1, 2),
+                                                           padding=(2, 1), dilation=(2, 1), dilation_patch=(1, 2)))}
+    blob = {}
+    for name, c in cases.items():
+        a = torch.randn(c["shape"], generator=g, requires_grad=True)
+        b = torch.randn(c["shape"], generator=g, requires_grad=True)
+        out = spatial_correlation_sample(a, b, **c["kw"])
+        go = torch.randn(out.shape, generator=g)
+        (out * go).sum().backward()
+        blob.update({f"{name}_in1": _np(a), f"{name}_in2": _np(b), f"{name}_out": _np(out), f"{name}_gout": _np(go),
+                     f"{name}_g1": _np(a.grad), f"{name}_g2": _np(b.grad)})
+        blob[f"{name}_kw"] = np.frombuffer(json.dumps(c["kw"]).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT / "scs.npz", **blob)
+
+
+def golden_objective():
+    import attack_PCFA
+    from helper_functions import losses
+    g = torch.Generator().manual_seed(13)
+    B, H, W = 2, 12, 14
+    eps = 1e-7
+    blob = {}
+    img1 = torch.rand(B, 3, H, W, generator=g)
+    img2 = torch.rand(B, 3, H, W, generator=g)
+    img1[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.0, 1.0])          # saturated pixels (|w| ~ 8.3)
+    pred = 3 * torch.randn(B, 2, H, W, generator=g)
+    target = torch.randn(B, 2, H, W, generator=g)
+    pred[0, :, 0, 0] = target[0, :, 0, 0] + 1e-3
+    gnet1 = torch.randn(B, 3, H, W, generator=g)
+    gnet2 = torch.randn(B, 3, H, W, generator=g)
+    blob.update(img1=_np(img1), img2=_np(img2), pred=_np(pred), target=_np(target), gnet1=_np(gnet1), gnet2=_np(gnet2))
+
+    def scaled(x, var_change):           # ScaledInputModel.forward pre-processing, own_models.py:72-85
+        if var_change:
+            x = (1. / 2.) * 1. / (1. - eps) * (torch.tanh(x) + (1 - eps))
+        return 255. * torch.clamp(x, 0., 1.)
+
+    # --- change of variables (disjoint default): w0 = atanh(...) perturbed
+    w1 = torch.atanh(2. * (1. - eps) * img1 - (1 - eps)) + 0.05 * torch.randn(B, 3, H, W, generator=g)
+    w2 = torch.atanh(2. * (1. - eps) * img2 - (1 - eps)) + 0.05 * torch.randn(B, 3, H, W, generator=g)
+    for lt in ("aee", "mse", "cosim"):
+        for mu, tag in ((2500. / 0.005, "act"), (0.0 + 5.0, "small")):
+            a, b = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+            p = pred.clone().requires_grad_(True)
+            d1, d2 = attack_PCFA.extract_deltas(a, b, img1, img2, "change_of_variables", eps_box=eps)
+            bound = 0.005 if tag == "act" else 10.0
+            loss = losses.loss_delta_constraint(p, target, d1, d2, torch.device("cpu"), delta_bound=bound, mu=mu, f_type=lt)
+            total = loss + (scaled(a, True) * gnet1).sum() + (scaled(b, True) * gnet2).sum()
+            total.backward()
+            blob.update({f"cov_{lt}_{tag}_loss": _np(loss), f"cov_{lt}_{tag}_gw1": _np(a.grad),
+                         f"cov_{lt}_{tag}_gw2": _np(b.grad), f"cov_{lt}_{tag}_gpred": _np(p.grad)})
+    blob.update(cov_w1=_np(w1), cov_w2=_np(w2), cov_net1=_np(scaled(w1, True)),
+                cov_d1=_np(attack_PCFA.extract_deltas(w1, w2, img1, img2, "change_of_variables", eps_box=eps)[0]))
+    # --- clipping (disjoint)
+    c1 = img1 + 0.3 * torch.randn(B, 3, H, W, generator=g)
+    c2 = img2 + 0.3 * torch.randn(B, 3, H, W, generator=g)
+    a, b = c1.clone().requires_grad_(True), c2.clone().requires_grad_(True)
+    d1, d2 = attack_PCFA.extract_deltas(a, b, img1, img2, "clipping", eps_box=eps)
+    loss = losses.loss_delta_constraint(pred, target, d1, d2, torch.device("cpu"), delta_bound=0.005, mu=5e5, f_type="aee")
+    (loss + (scaled(a, False) * gnet1).sum() + (scaled(b, False) * gnet2).sum()).backward()
+    blob.update(clip_v1=_np(c1), clip_v2=_np(c2), clip_loss=_np(loss), clip_g1=_np(a.grad), clip_g2=_np(b.grad),
+                clip_net1=_np(scaled(c1, False)), clip_d1=_np(d1))
+    # --- joint per pair (clipping): x_k = clamp(I_k + delta), penalty on extract_deltas_joint
+    dj = 0.3 * torch.randn(B, 3, H, W, generator=g)
+    imax, imin = torch.max(img1, img2), torch.min(img1, img2)
+    a = dj.clone().requires_grad_(True)
+    d1, d2 = attack_PCFA.extract_deltas_joint(a, imax, imin)
+    loss = losses.loss_delta_constraint(pred, target, d1, d2, torch.device("cpu"), delta_bound=0.005, mu=5e5, f_type="aee")
+    (loss + (scaled(img1 + a, False) * gnet1).sum() + (scaled(img2 + a, False) * gnet2).sum()).backward()
+    blob.update(joint_v=_np(dj), joint_loss=_np(loss), joint_g=_np(a.grad), joint_d=_np(d1),
+                joint_net2=_np(scaled(img2 + dj, False)))
+    # --- universal: one delta per image slot broadcast over the batch, penalty on the raw delta
+    u1 = 0.05 * torch.randn(3, H, W, generator=g)
+    u2 = 0.05 * torch.randn(3, H, W, generator=g)
+    a, b = u1.clone().requires_grad_(True), u2.clone().requires_grad_(True)
+    n1 = scaled(img1 + a.repeat([B, 1, 1, 1]), False)
+    n2 = scaled(img2 + b.repeat([B, 1, 1, 1]), False)
+    loss = losses.loss_delta_constraint(pred, target, a, b, torch.device("cpu"), delta_bound=0.005, mu=5e5, f_type="aee")
+    (loss + (n1 * gnet1).sum() + (n2 * gnet2).sum()).backward()
+    blob.update(uni_v1=_np(u1), uni_v2=_np(u2), uni_loss=_np(loss), uni_g1=_np(a.grad), uni_g2=_np(b.grad),
+                uni_net1=_np(n1))
+    a = u1.clone().requires_grad_(True)                                   # universal + joint
+    n1 = scaled(img1 + a.repeat([B, 1, 1, 1]), False)
+    n2 = scaled(img2 + a.repeat([B, 1, 1, 1]), False)
+    loss = losses.loss_delta_constraint(pred, target, a, a, torch.device("cpu"), delta_bound=0.005, mu=5e5, f_type="aee")
+    (loss + (n1 * gnet1).sum() + (n2 * gnet2).sum()).backward()
+    blob.update(unij_loss=_np(loss), unij_g=_np(a.grad))
+    np.savez_compressed(OUT / "objective.npz", **blob)
+
+
+def golden_pwc_warp():
+    from models.PWCNet.PWCNet import PWCDCNet
+    net = PWCDCNet.__new__(PWCDCNet)          # warp() uses no parameters
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 5, 9, 12, generator=g, requires_grad=True)
+    flo = (4.0 * torch.randn(2, 2, 9, 12, generator=g)).requires_grad_(True)
+    out = PWCDCNet.warp(net, x, flo)
+    go = torch.randn(out.shape, generator=g)
+    (out * go).sum().backward()
+    np.savez_compressed(OUT / "pwc_warp.npz", x=_np(x), flow=_np(flo), out=_np(out), gout=_np(go),
+                        gx=_np(x.grad), gflow=_np(flo.grad))
+
+
+def golden_raft():
+    """Full reference RAFT (12 iters) forward + backward to the images with name-keyed weights."""
+    from models.raft.raft import RAFT
+    sys.path.insert(0, str(REPO))
+    from pcfa_b200.networks.weights import deterministic_state_, synthetic_pair
+    cfg = json.load(open(REF / "models/_config/raft_config.json"))
+    net = deterministic_state_(RAFT(dict(cfg)), seed=0).eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    i1, i2 = synthetic_pair(0, 128, 160)
+    i1.requires_grad_(True); i2.requires_grad_(True)
+    flow_lo, flow_up = net(i1, i2, iters=12, test_mode=True)
+    go = torch.randn(flow_up.shape, generator=torch.Generator().manual_seed(15)) / flow_up.numel()
+    (flow_up * go).sum().backward()
+    np.savez_compressed(OUT / "raft_e2e.npz", flow_lo=_np(flow_lo), flow_up=_np(flow_up), gout=_np(go),
+                        g_img1=_np(i1.grad), g_img2=_np(i2.grad))
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    _shim_reference()
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft):
+        fn()
+        print("wrote", fn.__name__)
+
+
+if __name__ == "__main__":
+    main()

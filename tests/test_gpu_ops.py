@@ -1,0 +1,273 @@
+"""Parity tests proper: every CUDA operator, called through the C ABI (ctypes → libpcfa_b200.so),
+against the oracle on seeded inputs and against the committed reference outputs (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, kw_of
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(rtol=1e-3, atol_rms=1e-3)       # BASELINE.json: rtol 1e-3 on fp32 cost volumes and flows
+TIGHT = dict(rtol=1e-4, atol_rms=1e-4)
+
+
+def cu(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------- CorrBlock
+@pytest.mark.parametrize("impl", [1, 0])
+def test_corrblock_matches_reference_outputs(golden, impl, monkeypatch):
+    from pcfa_b200.corr_block import CorrBlock
+    monkeypatch.setenv("PCFA_CORR_IMPL", str(impl))
+    z = golden("corrblock")
+    f1, f2 = cu(z["fmap1"], True), cu(z["fmap2"], True)
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    N = f1.shape[0] * f1.shape[2] * f1.shape[3]
+    assert [tuple(p.shape) for p in blk.corr_pyramid] == [(N, 1, 16, 24), (N, 1, 8, 12), (N, 1, 4, 6), (N, 1, 2, 3)]
+    for l in (1, 2, 3):
+        assert_close(npy(blk.corr_pyramid[l]), z[f"level{l}"], what=f"level {l}", **TOL)
+    assert_close(npy(blk.corr_pyramid[0])[::37], z["level0_rows"], what="level 0", **TOL)
+    out_a = blk(cu(z["coords_a"]))
+    out_b = blk(cu(z["coords_b"]))
+    assert out_a.is_contiguous() and out_a.dtype == torch.float32
+    assert_close(npy(out_a), z["out_a"], what="lookup a", **TOL)
+    assert_close(npy(out_b), z["out_b"], what="lookup b (out-of-range taps)", **TOL)
+    (out_a * cu(z["gout_a"])).sum().backward(retain_graph=True)
+    assert_close(npy(f1.grad), z["g1_a"], what="g fmap1", **TOL)
+    assert_close(npy(f2.grad), z["g2_a"], what="g fmap2", **TOL)
+    (out_b * cu(z["gout_b"])).sum().backward()
+    assert_close(npy(f1.grad), z["g1_ab"], what="g fmap1 accumulated", **TOL)
+    assert_close(npy(f2.grad), z["g2_ab"], what="g fmap2 accumulated", **TOL)
+
+
+@pytest.mark.parametrize("shape,levels,radius", [((2, 32, 18, 27), 4, 4), ((1, 64, 9, 17), 3, 3),
+                                                 ((3, 16, 8, 8), 2, 4), ((1, 128, 23, 40), 4, 4)])
+def test_corrblock_vs_oracle_ragged_shapes(shape, levels, radius):
+    from oracle import ops as O
+    from pcfa_b200.corr_block import CorrBlock
+    g = np.random.default_rng(sum(shape))
+    B, C, H, W = shape
+    f1 = g.standard_normal(shape).astype(np.float32)
+    f2 = g.standard_normal(shape).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 4 * g.standard_normal((B, 2, H, W))).astype(np.float32)
+    t1, t2 = cu(f1, True), cu(f2, True)
+    blk = CorrBlock(t1, t2, num_levels=levels, radius=radius)
+    pyr = O.corr_pyramid_forward(f1, f2, levels)
+    assert_close(npy(blk._flat), pyr, what="pyramid", **TOL)
+    out = blk(cu(coords))
+    assert_close(npy(out), O.corr_lookup_forward(pyr, coords, levels, radius), what="lookup", **TOL)
+    go = g.standard_normal(out.shape).astype(np.float32)
+    (out * cu(go)).sum().backward()
+    gp = O.corr_lookup_backward(go, coords, levels, radius)
+    g1, g2 = O.corr_pyramid_backward(gp, f1, f2, levels)
+    assert_close(npy(t1.grad), g1, what="g fmap1", **TOL)
+    assert_close(npy(t2.grad), g2, what="g fmap2", **TOL)
+
+
+def test_corr_static_and_forward_only():
+    from pcfa_b200.corr_block import CorrBlock
+    g = torch.Generator().manual_seed(0)
+    f1 = torch.randn(1, 16, 6, 10, generator=g).cuda()
+    f2 = torch.randn(1, 16, 6, 10, generator=g).cuda()
+    c = CorrBlock.corr(f1, f2)
+    assert c.shape == (1, 6, 10, 1, 6, 10)
+    ref = torch.matmul(f1.view(1, 16, 60).transpose(1, 2), f2.view(1, 16, 60)).view(1, 6, 10, 1, 6, 10) / 4.0
+    assert_close(npy(c), npy(ref), what="CorrBlock.corr", **TOL)
+    with torch.no_grad():
+        blk = CorrBlock(f1, f2, num_levels=2, radius=2)
+        out = blk(torch.zeros(1, 2, 6, 10).cuda())
+    assert out.shape == (1, 2 * 25, 6, 10)
+
+
+# ----------------------------------------------------------------------------------- SCS / PWC
+def test_scs_matches_reference_outputs(golden):
+    from pcfa_b200.spatial_correlation_sampler import SpatialCorrelationSampler, spatial_correlation_sample
+    z = golden("scs")
+    for name in ("pwc", "fn2like", "general", "dilated"):
+        kw = kw_of(z, name)
+        a, b = cu(z[f"{name}_in1"], True), cu(z[f"{name}_in2"], True)
+        out = spatial_correlation_sample(a, b, **kw)
+        assert_close(npy(out), z[f"{name}_out"], what=f"scs fwd {name}", **TOL)
+        (out * cu(z[f"{name}_gout"])).sum().backward()
+        assert_close(npy(a.grad), z[f"{name}_g1"], what=f"scs g1 {name}", **TOL)
+        assert_close(npy(b.grad), z[f"{name}_g2"], what=f"scs g2 {name}", **TOL)
+        out2 = SpatialCorrelationSampler(**kw)(a.detach(), b.detach())
+        assert torch.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize("C,H,W", [(196, 6, 20), (128, 12, 40), (96, 24, 80), (32, 17, 37)])
+def test_pwc_correlate_vs_oracle(C, H, W):
+    from oracle import ops as O
+    from pcfa_b200.spatial_correlation_sampler import pwc_correlate
+    g = np.random.default_rng(C + H)
+    a = g.standard_normal((2, C, H, W)).astype(np.float32)
+    b = g.standard_normal((2, C, H, W)).astype(np.float32)
+    ta, tb = cu(a, True), cu(b, True)
+    out = pwc_correlate(ta, tb)
+    ref = O.scs_forward(a, b, 1, 9).reshape(2, 81, H, W) / C
+    assert_close(npy(out), ref, what="pwc correlate", **TOL)
+    go = g.standard_normal(ref.shape).astype(np.float32)
+    (out * cu(go)).sum().backward()
+    g1, g2 = O.scs_backward(a, b, go.reshape(2, 9, 9, H, W) / C, 1, 9)
+    assert_close(npy(ta.grad), g1, what="pwc g1", **TOL)
+    assert_close(npy(tb.grad), g2, what="pwc g2", **TOL)
+
+
+def test_pwc_warp_matches_reference_outputs(golden):
+    from pcfa_b200.pwc_warp import pwc_warp
+    z = golden("pwc_warp")
+    x, f = cu(z["x"], True), cu(z["flow"], True)
+    out = pwc_warp(x, f)
+    assert_close(npy(out), z["out"], what="warp", **TIGHT)
+    (out * cu(z["gout"])).sum().backward()
+    assert_close(npy(x.grad), z["gx"], what="warp gx", **TIGHT)
+    assert_close(npy(f.grad), z["gflow"], what="warp gflow", rtol=1e-3, atol_rms=1e-3)
+
+
+# ----------------------------------------------------------------------------------- FlowNet2 ops
+@pytest.mark.parametrize("cfg", [dict(pad=20, ks=1, md=20, s1=1, s2=2), dict(pad=4, ks=1, md=4, s1=1, s2=1),
+                                 dict(pad=6, ks=3, md=4, s1=1, s2=2), dict(pad=4, ks=1, md=4, s1=2, s2=2)])
+def test_fn2_correlation_vs_oracle(cfg):
+    from oracle import ops as O
+    from pcfa_b200.flownet2_ops import Correlation
+    g = np.random.default_rng(cfg["pad"] * 7 + cfg["ks"])
+    a = g.standard_normal((2, 12, 14, 19)).astype(np.float32)
+    b = g.standard_normal((2, 12, 14, 19)).astype(np.float32)
+    ta, tb = cu(a, True), cu(b, True)
+    m = Correlation(pad_size=cfg["pad"], kernel_size=cfg["ks"], max_displacement=cfg["md"], stride1=cfg["s1"],
+                    stride2=cfg["s2"], corr_multiply=1)
+    out = m(ta, tb)
+    ref = O.fn2corr_forward(a, b, **cfg)
+    assert_close(npy(out), ref, what="fn2 corr fwd", **TOL)
+    go = g.standard_normal(ref.shape).astype(np.float32)
+    (out * cu(go)).sum().backward()
+    g1, g2 = O.fn2corr_backward(a, b, go, **cfg)
+    assert_close(npy(ta.grad), g1, what="fn2 corr g1", **TOL)
+    assert_close(npy(tb.grad), g2, what="fn2 corr g2", **TOL)
+
+
+def test_resample2d_and_channelnorm_vs_oracle():
+    from oracle import ops as O
+    from pcfa_b200.flownet2_ops import ChannelNorm, Resample2d
+    g = np.random.default_rng(21)
+    img = g.standard_normal((2, 3, 24, 40)).astype(np.float32)
+    flow = (6 * g.standard_normal((2, 2, 24, 40))).astype(np.float32)     # leaves the image on all sides
+    ti, tf = cu(img, True), cu(flow, True)
+    out = Resample2d()(ti, tf)
+    assert_close(npy(out), O.resample2d_forward(img, flow), what="resample2d fwd", **TIGHT)
+    go = g.standard_normal(img.shape).astype(np.float32)
+    (out * cu(go)).sum().backward()
+    gi, gf = O.resample2d_backward(img, flow, go)
+    assert_close(npy(ti.grad), gi, what="resample2d g img (trunc quirk)", **TIGHT)
+    assert_close(npy(tf.grad), gf, what="resample2d g flow", **TIGHT)
+    near = Resample2d(bilinear=False)(ti.detach(), tf.detach())
+    assert_close(npy(near), O.resample2d_forward(img, flow, bilinear=False), what="nearest", **TIGHT)
+    for C in (2, 3):
+        x = g.standard_normal((2, C, 24, 40)).astype(np.float32)
+        tx = cu(x, True)
+        o = ChannelNorm()(tx)
+        ref = O.channelnorm_forward(x)
+        assert_close(npy(o), ref, what="channelnorm", **TIGHT)
+        go = g.standard_normal(ref.shape).astype(np.float32)
+        (o * cu(go)).sum().backward()
+        assert_close(npy(tx.grad), O.channelnorm_backward(x, ref, go), what="channelnorm bwd", **TIGHT)
+
+
+# ----------------------------------------------------------------------------------- objective
+def test_objective_kernels_match_reference_outputs(golden):
+    from pcfa_b200 import objective as J
+    z = golden("objective")
+    eps = 1e-7
+    img1, img2 = cu(z["img1"]), cu(z["img2"])
+    pred, target = cu(z["pred"]), cu(z["target"])
+    gnet1, gnet2 = cu(z["gnet1"]), cu(z["gnet2"])
+
+    def run(mode, joint, v1, v2, lt, mu, bound):
+        fo = J.FusedObjective(lambda a, b: (a.sum() * 0 + b.sum() * 0) + pred, img1, img2, target, mode=mode,
+                              joint=joint, pad=(0, 0), eps_box=eps, scale=255.0, delta_bound=bound, mu=mu, loss=lt)
+        fo._forward_boxes(v1, v2, True)
+        fo._loss(pred, True)
+        g1 = torch.empty_like(v1)
+        J._box_backward(v1, img1, fo.amax, fo.amin, gnet1, fo.terms, g1, False, mode, eps, 255.0)
+        if joint:
+            J._box_backward(v1, img2, fo.amax, fo.amin, gnet2, fo.terms, g1, True, mode, eps, 255.0)
+            return fo, g1, None
+        g2 = torch.empty_like(v2)
+        J._box_backward(v2, img2, fo.amax, fo.amin, gnet2, fo.terms, g2, False, mode, eps, 255.0)
+        return fo, g1, g2
+
+    w1, w2 = cu(z["cov_w1"]), cu(z["cov_w2"])
+    for lt in ("aee", "mse", "cosim"):
+        for tag, mu, bound in (("act", 2500. / 0.005, 0.005), ("small", 5.0, 10.0)):
+            fo, g1, g2 = run(J.BOX_COV, False, w1, w2, lt, mu, bound)
+            np.testing.assert_allclose(float(fo.terms[0]), float(z[f"cov_{lt}_{tag}_loss"]), rtol=1e-4)
+            assert_close(npy(fo.gflow), z[f"cov_{lt}_{tag}_gpred"], what=f"gpred {lt} {tag}", **TIGHT)
+            assert_close(npy(g1), z[f"cov_{lt}_{tag}_gw1"], what=f"gw1 {lt} {tag}", **TOL)
+            assert_close(npy(g2), z[f"cov_{lt}_{tag}_gw2"], what=f"gw2 {lt} {tag}", **TOL)
+    assert_close(npy(fo.net_in1), z["cov_net1"], what="cov net_in", **TIGHT)
+    assert_close(npy(fo.delta1), z["cov_d1"], what="cov delta", rtol=1e-3, atol_rms=1e-4)
+
+    fo, g1, g2 = run(J.BOX_CLIP, False, cu(z["clip_v1"]), cu(z["clip_v2"]), "aee", 5e5, 0.005)
+    np.testing.assert_allclose(float(fo.terms[0]), float(z["clip_loss"]), rtol=1e-4)
+    assert_close(npy(g1), z["clip_g1"], what="clip g1", **TIGHT)
+    assert_close(npy(g2), z["clip_g2"], what="clip g2", **TIGHT)
+    assert_close(npy(fo.net_in1), z["clip_net1"], what="clip net", **TIGHT)
+
+    fo, g1, _ = run(J.BOX_JOINT, True, cu(z["joint_v"]), None, "aee", 5e5, 0.005)
+    np.testing.assert_allclose(float(fo.terms[0]), float(z["joint_loss"]), rtol=1e-4)
+    assert_close(npy(g1), z["joint_g"], what="joint g", **TIGHT)
+    assert_close(npy(fo.net_in2), z["joint_net2"], what="joint net2", **TIGHT)
+    assert_close(npy(fo.delta1), z["joint_d"], what="joint delta", **TIGHT)
+
+    fo, g1, g2 = run(J.BOX_UNIVERSAL, False, cu(z["uni_v1"]), cu(z["uni_v2"]), "aee", 5e5, 0.005)
+    np.testing.assert_allclose(float(fo.terms[0]), float(z["uni_loss"]), rtol=1e-4)
+    assert_close(npy(g1), z["uni_g1"], what="universal g1", **TIGHT)
+    assert_close(npy(g2), z["uni_g2"], what="universal g2", **TIGHT)
+    fo, g1, _ = run(J.BOX_UNIVERSAL, True, cu(z["uni_v1"]), None, "aee", 5e5, 0.005)
+    np.testing.assert_allclose(float(fo.terms[0]), float(z["unij_loss"]), rtol=1e-4)
+    assert_close(npy(g1), z["unij_g"], what="universal joint g", **TIGHT)
+
+
+def test_reference_shaped_objective_functions(golden):
+    """extract_deltas / loss_delta_constraint / scaled_input with autograd, as the reference composes them."""
+    from pcfa_b200 import objective as J
+    z = golden("objective")
+    eps = 1e-7
+    img1, img2 = cu(z["img1"]), cu(z["img2"])
+    a, b = cu(z["cov_w1"], True), cu(z["cov_w2"], True)
+    p = cu(z["pred"], True)
+    d1, d2 = J.extract_deltas(a, b, img1, img2, "change_of_variables", eps_box=eps)
+    loss = J.loss_delta_constraint(p, cu(z["target"]), d1, d2, None, delta_bound=0.005, mu=2500. / 0.005, f_type="aee")
+    n1 = J.scaled_input(a, var_change=True, eps_box=eps, make_unit_input=True)
+    n2 = J.scaled_input(b, var_change=True, eps_box=eps, make_unit_input=True)
+    (loss + (n1 * cu(z["gnet1"])).sum() + (n2 * cu(z["gnet2"])).sum()).backward()
+    np.testing.assert_allclose(float(loss), float(z["cov_aee_act_loss"]), rtol=1e-4)
+    assert_close(npy(a.grad), z["cov_aee_act_gw1"], what="gw1", **TOL)
+    assert_close(npy(b.grad), z["cov_aee_act_gw2"], what="gw2", **TOL)
+    assert_close(npy(p.grad), z["cov_aee_act_gpred"], what="gpred", **TIGHT)
+    dj = cu(z["joint_v"], True)
+    e1, e2 = J.extract_deltas_joint(dj, torch.max(img1, img2), torch.min(img1, img2))
+    assert e1 is e2
+    assert_close(npy(e1), z["joint_d"], what="joint delta", **TIGHT)
+    with pytest.raises(NotImplementedError):
+        J.loss_delta_constraint(p, p, d1, d2, f_type="l1")
+    with pytest.raises(ValueError):
+        J.box_mode("change_of_variables", joint=True)
+
+
+def test_no_cpu_fallback():
+    from pcfa_b200.corr_block import CorrBlock
+    from pcfa_b200.spatial_correlation_sampler import spatial_correlation_sample
+    x = torch.randn(1, 4, 8, 8)
+    with pytest.raises(RuntimeError):
+        CorrBlock(x, x)
+    with pytest.raises(RuntimeError):
+        spatial_correlation_sample(x, x, patch_size=3)
