@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — PCFA closure evaluations per second (forward + backward through the flow network).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one PCFA closure evaluation: box transform → network forward → unpad →
+loss + penalty → backward to the perturbation variables.  Workload at every N: BASELINE.json
+configs[1] — RAFT (12 GRU iterations, 4-level all-pairs pyramid), disjoint perturbations with the
+change-of-variables box constraint, zero target, AEE loss, one Sintel-shaped 436x1024 pair per GPU
+(weak scaling: pairs are independent, no data-path collective).  Weights are deterministic synthetic
+values and the pair is synthetic (no network access for checkpoints/datasets).
+
+Prints ONE JSON line (see the task contract): value = closures/s with inputs resident in HBM and
+the closure replayed from a CUDA graph; e2e = the same through the public API with host buffers
+(H2D of the pair and D2H of the loss inside the timed region); roofline = the dominant pcfa_b200
+kernel measured with CUDA events in an instrumented eager pass; cpu_baseline = the oracle port of
+the reference closure timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "pcfa_closure_evals_per_sec"
+UNIT = "closures/s"
+H_IMG, W_IMG = 436, 1024
+DELTA_BOUND, EPS_BOX = 0.005, 1e-7
+MU = 2500.0 / DELTA_BOUND           # attack_PCFA.py:578-583, zero target
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=3)
+    ap.add_argument("--height", type=int, default=H_IMG)
+    ap.add_argument("--width", type=int, default=W_IMG)
+    return ap.parse_args()
+
+
+def config_dict(args, n):
+    return {"workload": "RAFT PCFA disjoint, change_of_variables, zero target, aee, delta_bound=0.005, "
+                        "12 GRU iters, 4-level all-pairs pyramid, %dx%d (padded 440x1024), batch 1 per GPU" % (args.height, args.width),
+            "pairs_per_gpu": 1, "parallelism": "pair-sharded x%d (no collective)" % n,
+            "l2": "per-step working set ~1.6 GB (261 MB pyramid + 261 MB gradient pyramid + activations) >> 126 MB L2, no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ workload
+def make_problem(device, rank, H, W, ops=None):
+    """Network + objective for one synthetic pair, exactly as pcfa_attack sets it up
+    (attack_PCFA.py:55-131): /255, pad, w = atanh(2(1-eps)I - (1-eps)), zero target."""
+    from pcfa_b200.adapter import build_network, preprocess_img
+    from pcfa_b200.networks.weights import synthetic_pair
+    net = build_network("RAFT", device=device, seed=0, ops=ops)
+    i1, i2 = synthetic_pair(rank, H, W)
+    return net, i1, i2
+
+
+def prepare_on_device(i1, i2, device):
+    from pcfa_b200.adapter import preprocess_img
+    a, b = i1.to(device, non_blocking=True) / 255.0, i2.to(device, non_blocking=True) / 255.0
+    padder, (a, b) = preprocess_img("RAFT", a, b)
+    return padder, a.contiguous(), b.contiguous()
+
+
+def init_vars(img):
+    return torch.atanh(2.0 * (1.0 - EPS_BOX) * img - (1 - EPS_BOX)).contiguous()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------ own arm
+def run_b200(args):
+    import torch.distributed as dist
+    from pcfa_b200 import _lib
+    from pcfa_b200 import objective as J
+    from pcfa_b200 import profiling
+    from pcfa_b200.adapter import preprocess_img
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    net, i1_host, i2_host = make_problem(device, rank, args.height, args.width)
+    i1_pin, i2_pin = i1_host.pin_memory(), i2_host.pin_memory()
+    padder, img1, img2 = prepare_on_device(i1_pin, i2_pin, device)
+    target = torch.zeros(1, 2, args.height, args.width, device=device)
+    fo = J.FusedObjective(lambda a, b: net(a, b, iters=12, test_mode=True)[1], img1, img2, target,
+                          mode=J.BOX_COV, joint=False, pad=padder.top_left, eps_box=EPS_BOX, scale=255.0,
+                          delta_bound=DELTA_BOUND, mu=MU, loss="aee")
+    w1, w2 = init_vars(img1), init_vars(img2)
+    w1 += 0.01 * torch.randn_like(w1)
+    w2 += 0.01 * torch.randn_like(w2)
+    g1, g2 = torch.empty_like(w1), torch.empty_like(w2)
+
+    def step():
+        return fo.evaluate(w1, w2, g1, g2)[0]
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    run = graph.replay if graph is not None else step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed region (inputs resident in HBM)
+    lc0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - lc0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            run()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with host buffers
+    loss_host = torch.empty(1).pin_memory()
+    d_i1, d_i2 = torch.empty_like(i1_pin, device=device), torch.empty_like(i2_pin, device=device)
+
+    def e2e_step():
+        d_i1.copy_(i1_pin, non_blocking=True)
+        d_i2.copy_(i2_pin, non_blocking=True)
+        _, (a, b) = preprocess_img("RAFT", d_i1 / 255.0, d_i2 / 255.0)
+        fo.image1.copy_(a)
+        fo.image2.copy_(b)
+        run()
+        loss_host.copy_(fo.terms[:1], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    t = torch.tensor([e2e_ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(t.item()) / 1e3)
+    h2d = i1_pin.numel() * 4 + i2_pin.numel() * 4
+
+    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": warm, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN convs with torch's default TF32; cost volume bf16x3-split or fp32 SIMT, fp32 accumulate)",
+           "data": "synthetic", "config": config_dict(args, world),
+           "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+           "cuda_graph": graph is not None, "clocks": clocks.summary(), "loss": float(fo.terms[0].item())}
+
+    if rank == 0:
+        # ---- per-kernel roofline, instrumented eager pass on the launching stream
+        peak, peak_src = peaks()
+        table = profiling.kernel_table(step, n_steps=3, B=1, C=256, H=img1.shape[2] // 8, W=img1.shape[3] // 8,
+                                       iters=12, peak_gbs=peak, img_numel=img1.numel(), flow_numel=2 * img1.shape[2] * img1.shape[3])
+        out["kernels"] = table
+        top = max(table, key=lambda r: r["total_us_per_step"]) if table else None
+        if top:
+            out["roofline"] = {"bound": "hbm", "kernel": top["name"], "achieved": top["achieved_gbs"], "peak": peak,
+                               "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": None,
+                               "peak_source": peak_src,
+                               "how": "CUDA events around each launch in an eager pass of the same step (graph replay cannot be event-bracketed per kernel)"}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, samples=args.cpu_samples)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_closure_factory(args):
+    """The reference closure (attack_PCFA.py:175-189) restated with torch CPU ops: oracle port."""
+    from oracle import torch_ref as TR
+    from pcfa_b200.adapter import InputPadder, build_network
+    from pcfa_b200.networks.weights import synthetic_pair
+    net = build_network("RAFT", device="cpu", seed=0, ops=TR)
+    i1, i2 = synthetic_pair(0, args.height, args.width)
+    i1, i2 = i1 / 255.0, i2 / 255.0
+    padder = InputPadder(i1.shape)
+    i1, i2 = padder.pad(i1, i2)
+    target = torch.zeros(1, 2, args.height, args.width)
+    w1 = init_vars(i1).requires_grad_(True)
+    w2 = init_vars(i2).requires_grad_(True)
+
+    def closure():
+        w1.grad = None
+        w2.grad = None
+        x1 = TR.scaled_input(w1, var_change=True, eps_box=EPS_BOX, make_unit_input=True)
+        x2 = TR.scaled_input(w2, var_change=True, eps_box=EPS_BOX, make_unit_input=True)
+        flow = padder.unpad(net(x1, x2, iters=12, test_mode=True)[1])
+        d1, d2 = TR.extract_deltas(w1, w2, i1, i2, "change_of_variables", eps_box=EPS_BOX)
+        loss = TR.loss_delta_constraint(flow, target, d1, d2, None, delta_bound=DELTA_BOUND, mu=MU, f_type="aee")
+        loss.backward()
+        return float(loss)
+    return closure
+
+
+def cpu_baseline(args, samples=3):
+    closure = cpu_closure_factory(args)
+    closure()
+    ts = []
+    for _ in range(samples):
+        t0 = time.perf_counter()
+        closure()
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"value": round(1.0 / med, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d full-size closure evaluations (RAFT 12 iters, %dx%d, fwd+bwd) after 1 warm-up, median; "
+                      "torch CPU ops restating the reference closure (oracle/torch_ref.py), nproc=%d"
+                      % (samples, args.height, args.width, os.cpu_count())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    closure = cpu_closure_factory(args)
+    for _ in range(max(1, args.warmup)):
+        closure()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        closure()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, 1),
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "each step = one full-size closure evaluation on the host cores (oracle/torch_ref.py "
+                                   "restating the reference's torch CPU path; /root/reference is not on this box)"},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the pcfa_b200 arm has no CPU fallback "
+                             "(use --impl reference for the CPU baseline)")
+        run_b200(a)

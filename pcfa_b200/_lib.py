@@ -11,6 +11,8 @@ import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpcfa_b200.so"
 _lib = None
+_raw = None
+_profile = None        # None, or dict: entry point name -> list of (start_event, end_event)
 
 c_fp = C.c_void_p      # device pointers travel as void*
 c_i = C.c_int
@@ -77,8 +79,36 @@ def load():
         fn.argtypes = args
     if lib.pcfa_abi_version() != 1:
         raise RuntimeError("libpcfa_b200.so ABI version mismatch — rebuild")
-    _lib = lib
-    return lib
+    global _raw
+    _raw = lib
+    _lib = _LibProxy()
+    return _lib
+
+
+class _LibProxy:
+    """Attribute access returns the raw ctypes function, or — while profiling is enabled
+    (pcfa_b200.profiling) — a wrapper that brackets the call with CUDA events on the current stream."""
+
+    def __getattr__(self, name):
+        fn = getattr(_raw, name)
+        if _profile is None or not name.startswith("pcfa_") or fn.restype is not c_i:
+            return fn
+
+        def timed(*args):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args)
+            e1.record()
+            _profile.setdefault(name, []).append((e0, e1))
+            return r
+        return timed
+
+
+def set_profile(store):
+    """Enable (dict) or disable (None) per-call CUDA-event timing of the C-ABI entry points."""
+    global _profile
+    _profile = store
 
 
 def check(status: int, what: str = "") -> None:

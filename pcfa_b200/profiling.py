@@ -1,0 +1,65 @@
+"""Per-kernel device timing of the C-ABI entry points with CUDA events (on the launching stream), and
+the algorithmic-bytes model used for the roofline fractions (DESIGN.md "Kernels and rooflines")."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def algorithmic_bytes(name: str, *, B: int, C: int, H: int, W: int, levels: int = 4, radius: int = 4,
+                      img_numel: int = 0, flow_numel: int = 0):
+    """Minimum HBM bytes one launch of `name` must move, or None if not modelled.
+    H, W are the feature-map (1/8) sizes for the correlation kernels."""
+    N = H * W
+    pyr, h, w = 0, H, W
+    for _ in range(levels):
+        pyr += B * N * h * w
+        h, w = h // 2, w // 2
+    D, F = 2 * radius + 1, 2 * radius + 2
+    if name == "pcfa_corr_pyramid_forward":
+        return 4 * (2 * B * C * N + pyr)
+    if name == "pcfa_corr_pyramid_backward":
+        return 4 * (pyr + 4 * B * C * N)
+    if name == "pcfa_corr_lookup_forward":
+        return 4 * B * N * (levels * F * F + levels * D * D + 2)
+    if name == "pcfa_corr_lookup_backward":
+        return 4 * B * N * (levels * D * D + 2 + 2 * levels * F * F)
+    if name == "pcfa_box_forward":
+        return 4 * 3 * img_numel            # read var + image, write net_in
+    if name == "pcfa_box_backward":
+        return 4 * 4 * img_numel            # read var, image, grad_net_in; write grad_var
+    if name == "pcfa_objective_loss":
+        return 4 * 3 * flow_numel           # read flow + target, write grad_flow
+    return None
+
+
+def kernel_table(step_fn, n_steps: int, *, B: int, C: int, H: int, W: int, iters: int, peak_gbs: float,
+                 img_numel: int = 0, flow_numel: int = 0):
+    """Run `step_fn` n_steps times with event bracketing and return one row per entry point."""
+    store: dict = {}
+    step_fn()
+    torch.cuda.synchronize()
+    _lib.set_profile(store)
+    try:
+        for _ in range(n_steps):
+            step_fn()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_profile(None)
+    rows = []
+    for name, evs in store.items():
+        us = [a.elapsed_time(b) * 1e3 for a, b in evs]
+        per_step = len(us) / n_steps
+        avg = sum(us) / len(us)
+        ab = algorithmic_bytes(name, B=B, C=C, H=H, W=W, img_numel=img_numel, flow_numel=flow_numel)
+        row = {"name": name, "launches_per_step": per_step, "avg_us": round(avg, 2),
+               "total_us_per_step": round(avg * per_step, 1), "algorithmic_bytes": ab}
+        if ab:
+            row["achieved_gbs"] = round(ab / (avg * 1e-6) / 1e9, 1)
+            row["frac_of_hbm_peak"] = round(row["achieved_gbs"] / peak_gbs, 4)
+        else:
+            row["achieved_gbs"] = 0.0
+        rows.append(row)
+    rows.sort(key=lambda r: -r["total_us_per_step"])
+    return rows

@@ -1,0 +1,73 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pcfa_b200.h declares;
+argument validation (no compute) behaves as documented."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "pcfa_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcfa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pcfa_b200 import _build, _lib
+    _build.build()
+    raw = C.CDLL(str(_lib.lib_path()))
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(raw, n), f"libpcfa_b200.so does not export {n}"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+
+
+def test_status_strings_and_argument_errors():
+    from pcfa_b200 import _lib
+    lib = _lib.load()
+    assert lib.pcfa_abi_version() == 1
+    assert lib.pcfa_status_string(0) == b"ok"
+    assert b"workspace" in lib.pcfa_status_string(-4)
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.pcfa_corr_lookup_forward(None, None, None, 1, 8, 8, 4, 4, None) == -1
+    assert lib.pcfa_corr_pyramid_forward(None, None, None, None, 0, 1, 8, 8, 8, 4, 0, None) == -1
+    assert lib.pcfa_resample2d_forward(None, None, None, 1, 3, 8, 8, 8, 8, 1, 1, None) == -1
+    with pytest.raises(RuntimeError, match="status -1"):
+        _lib.check(-1, "x")
+
+
+def test_layout_and_size_helpers_match_reference_arithmetic():
+    from pcfa_b200 import _lib
+    from pcfa_b200.corr_block import pyramid_layout
+    offs, hs, ws = pyramid_layout(1, 55, 128, 4)          # Sintel 440x1024 / 8  
+    assert (hs, ws) == ([55, 27, 13, 6], [128, 64, 32, 16])
+    n = 55 * 128
+    assert offs == [0, n * 7040, n * (7040 + 27 * 64), n * (7040 + 27 * 64 + 13 * 32), n * (7040 + 27 * 64 + 13 * 32 + 96)]
+    assert offs[-1] * 4 == 261_324_800                    # 261.3 MB per sample
+    lib = _lib.load()
+    p = _lib.ScsParams(1, 1, 9, 9, 0, 0, 1, 1, 1, 1, 1, 1)
+    oh, ow = C.c_int(), C.c_int()
+    assert lib.pcfa_scs_output_size(24, 80, C.byref(p), C.byref(oh), C.byref(ow)) == 0
+    assert (oh.value, ow.value) == (24, 80)
+    p = _lib.ScsParams(3, 3, 5, 5, 1, 1, 1, 1, 2, 2, 2, 2)
+    lib.pcfa_scs_output_size(11, 12, C.byref(p), C.byref(oh), C.byref(ow))
+    assert (oh.value, ow.value) == ((11 + 2 - 3) // 2 + 1, (12 + 2 - 3) // 2 + 1)
+    oc = C.c_int()
+    assert lib.pcfa_fn2corr_output_size(48, 160, 20, 1, 20, 1, 2, C.byref(oc), C.byref(oh), C.byref(ow)) == 0
+    assert (oc.value, oh.value, ow.value) == (441, 48, 160)      # FlowNetC.py:26-31
+    assert lib.pcfa_fn2corr_output_size(48, 160, 3, 1, 20, 1, 2, C.byref(oc), C.byref(oh), C.byref(ow)) == -1
+
+
+def test_no_cpu_fallback_on_cpu_tensors():
+    import torch
+    from pcfa_b200.corr_block import CorrBlock
+    from pcfa_b200.flownet2_ops import ChannelNorm
+    x = torch.randn(1, 4, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CorrBlock(x, x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ChannelNorm()(x)
