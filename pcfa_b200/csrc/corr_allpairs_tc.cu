@@ -1,9 +1,460 @@
-// tcgen05/TMEM all-pairs correlation with the pyramid pooling fused in the epilogue.
-// (placeholder until the tensor-core kernel lands: reports "unsupported" so the dispatcher uses SIMT)
+// All-pairs correlation pyramid on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   level_l[b*N + q, y, x] = (1/sqrt C) * <fmap1[b,:,q], pool_l(fmap2)[b,:,y,x]>      l = 0..levels-1
+//
+// (models/raft/corr.py:13-27,52-60).  avg_pool2d is linear, so pooling the *operand* (fmap2) and
+// correlating gives the same pyramid as correlating and pooling the 261 MB volume; every level is
+// therefore a plain GEMM tile and ONE persistent launch writes the whole pyramid exactly once —
+// no read-back of level 0, no separate pooling passes.
+//
+// Precision: fp32 features are split into bf16 hi + bf16 mid (a = hi + mid + O(2^-18 a)); the three
+// products hi*hi + hi*mid + mid*hi are accumulated in fp32 in TMEM, giving ~1e-5 relative error per
+// product — inside the 1e-3 parity bar with two orders of margin, at 1.5x the tensor work of TF32.
+//
+// Tile mapping: UMMA M = 128 *targets* (an 8 x 16 patch of level l, fetched by one 4-D TMA box from
+// the channel-last split copy of pool_l(fmap2), out-of-range rows/cols zero-filled), UMMA N = 128
+// *queries*.  TMEM lane == target, so an epilogue warp's 32 lanes are two 16-pixel row segments and
+// every global store instruction writes two full 64-byte runs of one query's row: coalesced without
+// staging through shared memory.  The 128-query operand (hi+mid, all channels: 128 KB) stays
+// resident in shared memory while the CTA sweeps target tiles; the target operand streams through a
+// 3-stage TMA/mbarrier ring.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
+// 2 = TMEM allocator, 4..7 = epilogue (TMEM -> registers -> global), double-buffered accumulators.
 #include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
 namespace pcfa {
-bool corr_pyramid_tc_supported(int, int, int, int, int) { return false; }
-int64_t corr_pyramid_tc_workspace_bytes(int, int, int, int, int) { return 0; }
-int corr_pyramid_forward_tc(const float*, const float*, float*, void*, int64_t, int, int, int, int,
-                            int, cudaStream_t) { return PCFA_E_BADARG; }
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
+constexpr int TC_PH = 8, TC_PW = 16;          // target patch
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 256;
+constexpr int TC_TILE_BYTES = 128 * 128;      // one [128 rows x 64 bf16] SW128 tile
+constexpr int TC_MAX_KCHUNKS = 4;             // C <= 256
+constexpr int TC_MAX_LEVELS = 4;
+
+struct TcMaps {
+    CUtensorMap q;                  // [C, N, 2B]            box {64, 128, 1}
+    CUtensorMap t[TC_MAX_LEVELS];   // [C, W_l, H_l, 2B]     box {64, 16, 8, 1}
+};
+
+struct TcParams {
+    int B, N, levels, kchunks, qblocks, tiles_per_qb;
+    int lh[TC_MAX_LEVELS], lw[TC_MAX_LEVELS], tiles_x[TC_MAX_LEVELS], tile_off[TC_MAX_LEVELS + 1];
+    long long lvl_off[TC_MAX_LEVELS];
+    long long total_tiles;
+    float scale;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1 KB).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address      bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (16 B; unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128.
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                ((uint32_t)(TC_BM >> 4) << 24);
+
+struct TileCoord { int b, qb, level, ty, tx; long long key; };
+__device__ __forceinline__ TileCoord decode_tile(long long t, const TcParams& P) {
+    TileCoord c;
+    c.key = t / P.tiles_per_qb;
+    int nt = (int)(t - c.key * P.tiles_per_qb);
+    c.b = (int)(c.key / P.qblocks);
+    c.qb = (int)(c.key - (long long)c.b * P.qblocks);
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < TC_MAX_LEVELS; ++i)
+        if (i < P.levels && nt >= P.tile_off[i]) l = i;
+    nt -= P.tile_off[l];
+    c.level = l;
+    c.ty = nt / P.tiles_x[l];
+    c.tx = nt - c.ty * P.tiles_x[l];
+    return c;
+}
+
+// ------------------------------------------------------------------------------------ main kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, float* __restrict__ pyr) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_q = base;                                        // [2][kchunks] tiles
+    const uint32_t smem_a = base + 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES;   // [STAGES][2] tiles
+    const uint32_t bars = smem_a + TC_STAGES * 2 * TC_TILE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES;
+    const uint32_t bar_qfull = bars + 16 * TC_STAGES, bar_qempty = bar_qfull + 8;
+    const uint32_t bar_tfull = bar_qempty + 8, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_begin = P.total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = P.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        int stage = 0; uint32_t phase = 0, qphase = 0;
+        long long cur = -1;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const TileCoord c = decode_tile(t, P);
+            if (c.key != cur) {
+                mbar_wait(bar_qempty, qphase ^ 1);           // MMAs reading the previous query block retired
+                mbar_expect_tx(bar_qfull, 2 * P.kchunks * TC_TILE_BYTES);
+                for (int part = 0; part < 2; ++part)
+                    for (int kc = 0; kc < P.kchunks; ++kc)
+                        tma_load_3d(smem_q + (part * TC_MAX_KCHUNKS + kc) * TC_TILE_BYTES, &maps.q, bar_qfull,
+                                    kc * TC_BK, c.qb * TC_BN, part * P.B + c.b);
+                qphase ^= 1;
+                cur = c.key;
+            }
+            for (int kc = 0; kc < P.kchunks; ++kc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                mbar_expect_tx(bar_full + 8 * stage, 2 * TC_TILE_BYTES);
+                const uint32_t dst = smem_a + stage * 2 * TC_TILE_BYTES;
+                tma_load_4d(dst, &maps.t[c.level], bar_full + 8 * stage, kc * TC_BK, c.tx * TC_PW, c.ty * TC_PH, c.b);
+                tma_load_4d(dst + TC_TILE_BYTES, &maps.t[c.level], bar_full + 8 * stage, kc * TC_BK, c.tx * TC_PW,
+                            c.ty * TC_PH, P.B + c.b);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================================== MMA issuer
+        int stage = 0; uint32_t phase = 0, qphase = 0, acc = 0, accphase = 0;
+        long long cur = -1;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const long long key = t / P.tiles_per_qb;
+            if (key != cur) { mbar_wait(bar_qfull, qphase); qphase ^= 1; cur = key; }
+            mbar_wait(bar_tempty + 8 * acc, accphase ^ 1);   // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * TC_BN;
+            for (int kc = 0; kc < P.kchunks; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_a + stage * 2 * TC_TILE_BYTES, a_mid = a_hi + TC_TILE_BYTES;
+                const uint32_t b_hi = smem_q + kc * TC_TILE_BYTES, b_mid = smem_q + (TC_MAX_KCHUNKS + kc) * TC_TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                    const uint32_t ko = kk * 32;             // 16 bf16 = 32 bytes along K inside the swizzle row
+                    tc_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16, (kc | kk) != 0);
+                    tc_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16, 1);
+                    tc_mma_bf16(d_tmem, umma_desc_sw128(a_mid + ko), umma_desc_sw128(b_hi + ko), kIdescBf16, 1);
+                }
+                tc_commit(bar_empty + 8 * stage);            // frees the smem slot once these MMAs retire
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(bar_tfull + 8 * acc);
+            const bool last_of_block = (t + 1 == t_end) || ((t + 1) / P.tiles_per_qb != key);
+            if (last_of_block) tc_commit(bar_qempty);
+            acc ^= 1;
+            if (acc == 0) accphase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int ew = warp - 4;                               // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int p = ew * 32 + lane;                          // target index inside the 8x16 patch
+        const int yl = p / TC_PW, xl = p % TC_PW;
+        uint32_t acc = 0, accphase = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const TileCoord c = decode_tile(t, P);
+            const int Hl = P.lh[c.level], Wl = P.lw[c.level];
+            const int y = c.ty * TC_PH + yl, x = c.tx * TC_PW + xl;
+            const bool ok = (y < Hl) && (x < Wl);
+            const long long qstride = (long long)Hl * Wl;
+            const int q0 = c.qb * TC_BN;
+            float* out = pyr + P.lvl_off[c.level] + ((long long)c.b * P.N + q0) * qstride + (long long)y * Wl + x;
+            mbar_wait(bar_tfull + 8 * acc, accphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr + c0, v);
+                tc_wait_ld();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (q0 + c0 + j < P.N) __stcs(out + (long long)(c0 + j) * qstride, __uint_as_float(v[j]) * P.scale);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            acc ^= 1;
+            if (acc == 0) accphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// ------------------------------------------------------------------------------------ operand prep
+// src fp32 [B][C][n]  ->  dst bf16 [2][B][n][C]  (hi plane, then mid plane), via a 32x32 smem transpose.
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C, int n) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, i = n0 + tx;
+        tile[r][tx] = (c < C && i < n) ? src[((long long)b * C + c) * n + i] : 0.f;
+    }
+    __syncthreads();
+    const long long plane = (long long)B * n * C;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = n0 + r, c = c0 + tx;
+        if (i < n && c < C) {
+            const float v = tile[tx][r];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const long long o = ((long long)b * n + i) * C + c;
+            dst[o] = hi;
+            dst[plane + o] = mid;
+        }
+    }
+}
+
+__global__ void tc_avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int Hi,
+                                   int Wi, int Ho, int Wo) {
+    const long long total = R * Ho * Wo;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % Wo);
+        const int y = (int)((idx / Wo) % Ho);
+        const long long r = idx / ((long long)Wo * Ho);
+        const float* p = in + (r * Hi + 2 * y) * (long long)Wi + 2 * x;
+        out[idx] = 0.25f * ((p[0] + p[1]) + (p[Wi] + p[Wi + 1]));
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+struct TcWorkspace {       // byte offsets into the caller's workspace (all 1 KB aligned)
+    int64_t q_split, t_split[TC_MAX_LEVELS], pooled[TC_MAX_LEVELS], total;
+};
+
+static TcWorkspace tc_workspace(int B, int C, int H, int W, int levels) {
+    TcWorkspace w{};
+    auto align = [](int64_t v) { return (v + 1023) & ~(int64_t)1023; };
+    int64_t o = 0;
+    w.q_split = o; o = align(o + (int64_t)2 * B * H * W * C * 2);
+    int h = H, ww = W;
+    for (int l = 0; l < levels; ++l) {
+        w.t_split[l] = o; o = align(o + (int64_t)2 * B * h * ww * C * 2);
+        if (l > 0) { w.pooled[l] = o; o = align(o + (int64_t)B * C * h * ww * 4); }
+        h /= 2; ww /= 2;
+    }
+    w.total = o;
+    return w;
+}
+
+bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels) {
+    if (C % TC_BK != 0 || C / TC_BK > TC_MAX_KCHUNKS || levels > TC_MAX_LEVELS || levels < 1) return false;
+    if (B < 1 || 2 * (long long)B > 0x7fffffff) return false;
+    int h = H, w = W;
+    for (int l = 0; l < levels; ++l) { if (h < 1 || w < 1) return false; h /= 2; w /= 2; }
+    return encode_fn() != nullptr;
+}
+
+int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels) {
+    if (C % TC_BK != 0 || C / TC_BK > TC_MAX_KCHUNKS || levels > TC_MAX_LEVELS || levels < 1) return 0;
+    return tc_workspace(B, C, H, W, levels).total;
+}
+
+static int split_transpose(const float* src, __nv_bfloat16* dst, int B, int C, int n, cudaStream_t s) {
+    dim3 grid(ceil_div(n, 32), ceil_div(C, 32), B);
+    split_transpose_kernel<<<grid, 256, 0, s>>>(src, dst, B, C, n);
+    return after_launch();
+}
+
+int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyramid, void* ws, int64_t ws_bytes,
+                            int B, int C, int H, int W, int levels, cudaStream_t s) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return PCFA_E_NODEVICE;
+    const TcWorkspace wl = tc_workspace(B, C, H, W, levels);
+    if (!ws || ws_bytes < wl.total || (reinterpret_cast<uintptr_t>(ws) & 15)) return PCFA_E_WORKSPACE;
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+    const int N = H * W;
+    const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
+
+    // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
+    PCFA_TRY(split_transpose(fmap1, reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split), B, C, N, s));
+    const float* prev = fmap2;
+    for (int l = 0; l < levels; ++l) {
+        const float* cur = prev;
+        if (l > 0) {
+            float* pooled = reinterpret_cast<float*>(wsb + wl.pooled[l]);
+            const long long cnt = (long long)B * C * L.h[l] * L.w[l];
+            int blocks = (int)((cnt + 255) / 256);
+            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            tc_avgpool2_kernel<<<blocks, 256, 0, s>>>(prev, pooled, (long long)B * C, L.h[l - 1], L.w[l - 1], L.h[l], L.w[l]);
+            PCFA_TRY(after_launch());
+            cur = pooled;
+        }
+        PCFA_TRY(split_transpose(cur, reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]), B, C, L.h[l] * L.w[l], s));
+        prev = cur;
+    }
+
+    // ---- tensor maps
+    TcMaps maps;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(2 * B)};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)N * C * 2};
+        cuuint32_t box[3] = {TC_BK, TC_BN, 1}, es[3] = {1, 1, 1};
+        if (enc(&maps.q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wsb + wl.q_split, dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return PCFA_E_BADARG;
+    }
+    TcParams P{};
+    P.B = B; P.N = N; P.levels = levels; P.kchunks = C / TC_BK; P.qblocks = ceil_div(N, TC_BN);
+    P.scale = 1.0f / sqrtf((float)C);
+    int toff = 0;
+    for (int l = 0; l < levels; ++l) {
+        P.lh[l] = L.h[l]; P.lw[l] = L.w[l]; P.lvl_off[l] = L.off[l];
+        P.tiles_x[l] = ceil_div(L.w[l], TC_PW);
+        P.tile_off[l] = toff;
+        toff += P.tiles_x[l] * ceil_div(L.h[l], TC_PH);
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L.w[l], (cuuint64_t)L.h[l], (cuuint64_t)(2 * B)};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L.w[l] * C * 2, (cuuint64_t)L.h[l] * L.w[l] * C * 2};
+        cuuint32_t box[4] = {TC_BK, TC_PW, TC_PH, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&maps.t[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, wsb + wl.t_split[l], dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return PCFA_E_BADARG;
+    }
+    for (int l = levels; l < TC_MAX_LEVELS; ++l) maps.t[l] = maps.t[0];
+    P.tile_off[levels] = toff;
+    for (int l = levels + 1; l <= TC_MAX_LEVELS; ++l) P.tile_off[l] = toff;
+    P.tiles_per_qb = toff;
+    P.total_tiles = (long long)B * P.qblocks * toff;
+
+    const int smem = 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES + TC_STAGES * 2 * TC_TILE_BYTES + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        PCFA_CUDA_TRY(cudaGetDevice(&dev));
+        PCFA_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int grid = num_sms;
+    if ((long long)grid > P.total_tiles) grid = (int)P.total_tiles;
+    corr_pyramid_tc_kernel<<<grid, TC_THREADS, smem, s>>>(maps, P, pyramid);
+    return after_launch();
+}
+
 }  // namespace pcfa

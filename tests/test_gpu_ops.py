@@ -271,3 +271,45 @@ def test_no_cpu_fallback():
         CorrBlock(x, x)
     with pytest.raises(RuntimeError):
         spatial_correlation_sample(x, x, patch_size=3)
+
+
+# ----------------------------------------------------------------------------------- tcgen05 path
+def _build_pyramid(f1, f2, levels, impl):
+    from pcfa_b200 import _lib
+    from pcfa_b200.corr_block import pyramid_layout
+    lib = _lib.load()
+    B, C, H, W = f1.shape
+    offs, hs, ws = pyramid_layout(B, H, W, levels)
+    pyr = torch.full((offs[-1],), float("nan"), device="cuda")
+    wsb = lib.pcfa_corr_pyramid_workspace_bytes(B, C, H, W, levels)
+    wsp = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.pcfa_corr_pyramid_forward(_lib.ptr(f1), _lib.ptr(f2), _lib.ptr(pyr), _lib.ptr(wsp), wsb,
+                                             B, C, H, W, levels, impl, _lib.stream()), "pyramid fwd")
+    torch.cuda.synchronize()
+    return pyr, offs
+
+
+@pytest.mark.parametrize("shape,levels", [((1, 64, 16, 24), 4), ((2, 128, 18, 27), 4), ((1, 256, 9, 17), 3),
+                                          ((3, 64, 8, 8), 2), ((1, 256, 55, 128), 4), ((2, 256, 46, 62), 4)])
+def test_allpairs_tcgen05_matches_fp32_simt(shape, levels):
+    """bf16x3 tensor-core pyramid vs the exact-fp32 SIMT pyramid (which the oracle tests pin)."""
+    g = torch.Generator().manual_seed(sum(shape))
+    f1 = torch.randn(shape, generator=g).cuda() * 3
+    f2 = torch.randn(shape, generator=g).cuda() * 3
+    tc, offs = _build_pyramid(f1, f2, levels, 2)
+    simt, _ = _build_pyramid(f1, f2, levels, 1)
+    assert torch.isfinite(tc).all(), "tensor-core path left pyramid cells unwritten"
+    for l in range(levels):
+        a, b = tc[offs[l]:offs[l + 1]], simt[offs[l]:offs[l + 1]]
+        rms = float(b.pow(2).mean().sqrt())
+        err = float((a - b).abs().max())
+        assert err <= 1e-4 * rms + 1e-4 * float(b.abs().max()), f"level {l}: max err {err} (rms {rms})"
+
+
+def test_allpairs_tcgen05_vs_oracle_small():
+    from oracle import ops as O
+    g = np.random.default_rng(9)
+    f1 = g.standard_normal((1, 64, 12, 20)).astype(np.float32)
+    f2 = g.standard_normal((1, 64, 12, 20)).astype(np.float32)
+    tc, _ = _build_pyramid(cu(f1), cu(f2), 4, 2)
+    assert_close(npy(tc), O.corr_pyramid_forward(f1, f2, 4), what="tcgen05 pyramid vs oracle", **TIGHT)
