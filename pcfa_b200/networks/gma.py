@@ -1,0 +1,151 @@
+"""GMA (Jiang et al., ICCV 2021) around the B200 CorrBlock.
+
+Same architecture and state-dict keys as the reference's vendored network (models/gma/network.py:
+21-129, gma.py:34-115, update.py:112-139); the cost volume is this package's CorrBlock.  The
+reference evaluates GMA with 6 iterations and fp16 autocast on CUDA (ownutilities.py:327,
+models/_config/gma_config.json:5); both are kept.  As in networks/raft.py the mask head and convex
+upsampling only run for the prediction that test_mode returns.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch import einsum
+
+from .raft import BasicEncoder, BasicMotionEncoder, FlowHead, SepConvGRU, convex_upsample, coords_grid
+
+DEFAULT_CONFIG = {"epsilon": 1e-8, "num_heads": 1, "small": False, "mixed_precision": True,
+                  "position_only": False, "position_and_content": False}
+
+
+class RelPosEmb(nn.Module):
+    def __init__(self, max_pos_size, dim_head):
+        super().__init__()
+        self.rel_height = nn.Embedding(2 * max_pos_size - 1, dim_head)
+        self.rel_width = nn.Embedding(2 * max_pos_size - 1, dim_head)
+        deltas = torch.arange(max_pos_size).view(1, -1) - torch.arange(max_pos_size).view(-1, 1)
+        self.register_buffer('rel_ind', deltas + max_pos_size - 1)
+
+    def forward(self, q):
+        _, _, h, w, _ = q.shape
+        he = self.rel_height(self.rel_ind[:h, :h].reshape(-1)).view(h, h, 1, -1)     # (x u) d -> x u () d
+        we = self.rel_width(self.rel_ind[:w, :w].reshape(-1)).view(w, 1, w, -1)      # (y v) d -> y () v d
+        return einsum('b h x y d, x u v d -> b h x y u v', q, he) + einsum('b h x y d, y u v d -> b h x y u v', q, we)
+
+
+class Attention(nn.Module):
+    def __init__(self, *, position_only=False, position_and_content=False, dim, max_pos_size=100, heads=4, dim_head=128):
+        super().__init__()
+        self.position_only, self.position_and_content = position_only, position_and_content
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.to_qk = nn.Conv2d(dim, heads * dim_head * 2, 1, bias=False)
+        self.pos_emb = RelPosEmb(max_pos_size, dim_head)
+
+    def forward(self, fmap):
+        b, _, h, w = fmap.shape
+        q, k = self.to_qk(fmap).chunk(2, dim=1)
+        q = q.view(b, self.heads, -1, h, w).permute(0, 1, 3, 4, 2) * self.scale     # b h x y d
+        k = k.view(b, self.heads, -1, h, w).permute(0, 1, 3, 4, 2)
+        if self.position_only:
+            sim = self.pos_emb(q)
+        else:
+            sim = einsum('b h x y d, b h u v d -> b h x y u v', q, k)
+            if self.position_and_content:
+                sim = sim + self.pos_emb(q)
+        return sim.reshape(b, self.heads, h * w, h * w).softmax(dim=-1)
+
+
+class Aggregate(nn.Module):
+    def __init__(self, dim, heads=4, dim_head=128):
+        super().__init__()
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        inner = heads * dim_head
+        self.to_v = nn.Conv2d(dim, inner, 1, bias=False)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.project = nn.Conv2d(inner, dim, 1, bias=False) if dim != inner else None
+
+    def forward(self, attn, fmap):
+        b, _, h, w = fmap.shape
+        v = self.to_v(fmap).view(b, self.heads, -1, h * w).transpose(2, 3)          # b h (x y) d
+        out = einsum('b h i j, b h j d -> b h i d', attn, v)
+        out = out.transpose(2, 3).reshape(b, -1, h, w)                              # b (h d) x y
+        if self.project is not None:
+            out = self.project(out)
+        return fmap + self.gamma * out
+
+
+class GMAUpdateBlock(nn.Module):
+    def __init__(self, corr_levels, corr_radius, num_heads, hidden_dim=128):
+        super().__init__()
+        self.encoder = BasicMotionEncoder(corr_levels, corr_radius)
+        self.gru = SepConvGRU(hidden_dim=hidden_dim, input_dim=128 + hidden_dim + hidden_dim)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=256)
+        self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
+        self.aggregator = Aggregate(dim=128, dim_head=128, heads=num_heads)
+
+    def forward(self, net, inp, corr, flow, attention, want_mask=True):
+        motion = self.encoder(flow, corr)
+        motion_global = self.aggregator(attention, motion)
+        net = self.gru(net, torch.cat([inp, motion, motion_global], dim=1))
+        delta_flow = self.flow_head(net)
+        mask = 0.25 * self.mask(net) if want_mask else None
+        return net, mask, delta_flow
+
+
+class RAFTGMA(nn.Module):
+    def __init__(self, args=None, corr_block=None):
+        super().__init__()
+        cfg = dict(DEFAULT_CONFIG)
+        if args is not None:
+            cfg.update(vars(args) if not isinstance(args, dict) else args)
+        cfg.setdefault("dropout", 0)
+        cfg["corr_levels"], cfg["corr_radius"] = 4, 4
+        self.args = cfg
+        self.hidden_dim = self.context_dim = 128
+        self.fnet = BasicEncoder(output_dim=256, norm_fn='instance', dropout=cfg["dropout"])
+        self.cnet = BasicEncoder(output_dim=256, norm_fn='batch', dropout=cfg["dropout"])
+        self.update_block = GMAUpdateBlock(4, 4, cfg["num_heads"], hidden_dim=128)
+        self.att = Attention(position_only=cfg["position_only"], position_and_content=cfg["position_and_content"],
+                             dim=128, heads=cfg["num_heads"], max_pos_size=160, dim_head=128)
+        if corr_block is None:
+            from ..corr_block import CorrBlock as corr_block
+        self.corr_block = corr_block
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+        image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
+        image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
+        dev_type = image1.device.type
+        amp = bool(self.args["mixed_precision"]) and dev_type == "cuda"
+        with torch.autocast(dev_type, enabled=amp):
+            fmap1, fmap2 = self.fnet([image1, image2])
+        corr_fn = self.corr_block(fmap1.float(), fmap2.float(), radius=4)
+        with torch.autocast(dev_type, enabled=amp):
+            net, inp = torch.split(self.cnet(image1), [128, 128], dim=1)
+            net, inp = torch.tanh(net), torch.relu(inp)
+            attention = self.att(inp)
+        N, _, H, W = image1.shape
+        coords0 = coords_grid(N, H // 8, W // 8, image1.device)
+        coords1 = coords0.clone()
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        predictions, flow_up = [], None
+        for itr in range(iters):
+            coords1 = coords1.detach()
+            corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            need_up = (not test_mode) or itr == iters - 1
+            with torch.autocast(dev_type, enabled=amp):
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, attention, want_mask=need_up)
+            coords1 = coords1 + delta_flow
+            if need_up:
+                flow_up = convex_upsample(coords1 - coords0, up_mask)
+                predictions.append(flow_up)
+        if test_mode:
+            return coords1 - coords0, flow_up
+        return predictions
