@@ -57,8 +57,10 @@ int pcfa_corr_pyramid_layout(int B, int H, int W, int num_levels,
 /* Bytes of scratch needed by pcfa_corr_pyramid_forward / _backward for these sizes. */
 int64_t pcfa_corr_pyramid_workspace_bytes(int B, int C, int H, int W, int num_levels);
 
-/* impl: 0 = auto (tcgen05 path when C % 64 == 0, otherwise SIMT), 1 = force SIMT fp32,
- *       2 = force tcgen05 (bf16x3 split, fp32 accumulate in TMEM). */
+/* impl: 0 = auto (tcgen05 path when the shape qualifies, otherwise SIMT), 1 = force SIMT fp32,
+ *       2 = force tcgen05.  Forward: bf16 hi/mid split (3 products), fp32 accumulate in TMEM, needs
+ *       C % 64 == 0 and C <= 256.  Backward: TF32 gradient pyramid x TF32 hi/lo split features, needs
+ *       C % 16 == 0, C <= 256 and every level's H_l*W_l a multiple of 4 (TMA stride rule). */
 int pcfa_corr_pyramid_forward(const float* fmap1, const float* fmap2,
                               float* pyramid /* (overwritten) */,
                               void* workspace, int64_t workspace_bytes,

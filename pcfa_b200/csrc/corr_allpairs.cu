@@ -14,6 +14,11 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
                             cudaStream_t s);
 int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels);
+// --- tcgen05 backward (corr_allpairs_bwd_tc.cu) ----------------------------------------------
+int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
+                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s);
+int64_t corr_pyramid_bwd_tc_workspace_bytes(int B, int C, int H, int W, int levels);
+bool corr_pyramid_bwd_tc_supported(int B, int C, int H, int W, int levels);
 
 // 2x2 average pooling with floor output size over R independent images (F.avg_pool2d(x,2,2)).
 __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t R,
@@ -160,7 +165,9 @@ extern "C" int pcfa_corr_pyramid_layout(int B, int H, int W, int num_levels, int
 extern "C" int64_t pcfa_corr_pyramid_workspace_bytes(int B, int C, int H, int W, int num_levels) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || num_levels <= 0 || num_levels > 8) return 0;
     const int64_t simt = 2 * pooled_floats(B, C, H, W, num_levels) * (int64_t)sizeof(float);
-    const int64_t tc   = corr_pyramid_tc_workspace_bytes(B, C, H, W, num_levels);
+    const int64_t tcf  = corr_pyramid_tc_workspace_bytes(B, C, H, W, num_levels);
+    const int64_t tcb  = corr_pyramid_bwd_tc_workspace_bytes(B, C, H, W, num_levels);
+    const int64_t tc   = tcf > tcb ? tcf : tcb;
     const int64_t m    = simt > tc ? simt : tc;
     return m > 256 ? m : 256;
 }
@@ -195,7 +202,14 @@ extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float
                                           pcfa_stream_t stream) {
     if (!grad_pyramid || !fmap1 || !fmap2 || !grad_fmap1 || !grad_fmap2) return PCFA_E_BADARG;
     PCFA_TRY(pyramid_check(B, C, H, W, num_levels));
-    (void)impl;
+    const bool tc_ok = corr_pyramid_bwd_tc_supported(B, C, H, W, num_levels);
+    if (impl == 2 && !tc_ok) return PCFA_E_BADARG;
+    if (impl == 2 || (impl == 0 && tc_ok)) {
+        if (!workspace || workspace_bytes < corr_pyramid_bwd_tc_workspace_bytes(B, C, H, W, num_levels))
+            return PCFA_E_WORKSPACE;
+        return corr_pyramid_backward_tc(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace,
+                                        workspace_bytes, B, C, H, W, num_levels, as_stream(stream));
+    }
     const int64_t need = 2 * pooled_floats(B, C, H, W, num_levels) * (int64_t)sizeof(float);
     if (need > 0 && (!workspace || workspace_bytes < need)) return PCFA_E_WORKSPACE;
     return backward_simt(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2,

@@ -18,9 +18,9 @@
 // staging through shared memory.  The 128-query operand (hi+mid, all channels: 128 KB) stays
 // resident in shared memory while the CTA sweeps target tiles; the target operand streams through a
 // 3-stage TMA/mbarrier ring.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
-// 2 = TMEM allocator, 4..7 = epilogue (TMEM -> registers -> global), double-buffered accumulators.
-#include "common.cuh"
-#include <cuda.h>
+// 2 = TMEM allocator, 4..11 = epilogue (TMEM -> registers -> global), double-buffered accumulators.
+// The 1/sqrt(C) factor is folded into the query operand before the bf16 split.
+#include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -29,7 +29,7 @@ namespace pcfa {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
 constexpr int TC_PH = 8, TC_PW = 16;          // target patch
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;             // 4 control warps + 8 epilogue warps
 constexpr int TC_TILE_BYTES = 128 * 128;      // one [128 rows x 64 bf16] SW128 tile
 constexpr int TC_MAX_KCHUNKS = 4;             // C <= 256
 constexpr int TC_MAX_LEVELS = 4;
@@ -47,82 +47,6 @@ struct TcParams {
     float scale;
 };
 
-// ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded spin: a protocol bug traps (launch error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1 KB).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address      bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (16 B; unused for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128.
 constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                 ((uint32_t)(TC_BM >> 4) << 24);
@@ -165,7 +89,7 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -237,8 +161,9 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
             if (acc == 0) accphase ^= 1;
         }
     } else if (warp >= 4) {
-        // ===================================================================== epilogue
-        const int ew = warp - 4;                               // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        // ===================================================================== epilogue (8 warps)
+        // warp -> TMEM lanes [32*(warp%4), +32) (hardware rule) and query columns [64*half, +64).
+        const int ew = warp & 3, half = (warp - 4) >> 2;
         const int p = ew * 32 + lane;                          // target index inside the 8x16 patch
         const int yl = p / TC_PW, xl = p % TC_PW;
         uint32_t acc = 0, accphase = 0;
@@ -248,25 +173,32 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
             const int y = c.ty * TC_PH + yl, x = c.tx * TC_PW + xl;
             const bool ok = (y < Hl) && (x < Wl);
             const long long qstride = (long long)Hl * Wl;
-            const int q0 = c.qb * TC_BN;
+            const int q0 = c.qb * TC_BN + half * 64;
             float* out = pyr + P.lvl_off[c.level] + ((long long)c.b * P.N + q0) * qstride + (long long)y * Wl + x;
+            const int nq = min(64, P.N - q0);                  // valid queries in this half (<= 0: none)
             mbar_wait(bar_tfull + 8 * acc, accphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr + c0, v);
-                tc_wait_ld();
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (q0 + c0 + j < P.N) __stcs(out + (long long)(c0 + j) * qstride, __uint_as_float(v[j]) * P.scale);
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN + half * 64;
+            uint32_t v0[32], v1[32];
+            tc_ld32(taddr, v0);
+            tc_ld32(taddr + 32, v1);
+            tc_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);   // accumulator is in registers: release it early
+            if (ok) {
+                if (nq >= 64) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v0[j])); out += qstride; }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { if (j < nq) __stcs(out, __uint_as_float(v0[j])); out += qstride; }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { if (32 + j < nq) __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                }
+            }
             acc ^= 1;
             if (acc == 0) accphase ^= 1;
         }
@@ -282,13 +214,13 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
 // ------------------------------------------------------------------------------------ operand prep
 // src fp32 [B][C][n]  ->  dst bf16 [2][B][n][C]  (hi plane, then mid plane), via a 32x32 smem transpose.
 __global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C, int n) {
+split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C, int n, float scale) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
     for (int r = ty; r < 32; r += 8) {
         const int c = c0 + r, i = n0 + tx;
-        tile[r][tx] = (c < C && i < n) ? src[((long long)b * C + c) * n + i] : 0.f;
+        tile[r][tx] = (c < C && i < n) ? src[((long long)b * C + c) * n + i] * scale : 0.f;
     }
     __syncthreads();
     const long long plane = (long long)B * n * C;
@@ -319,11 +251,7 @@ __global__ void tc_avgpool2_kernel(const float* __restrict__ in, float* __restri
 }
 
 // ------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tc_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -337,6 +265,18 @@ static EncodeTiledFn encode_fn() {
             cudaGetLastError();
     }
     return fn;
+}
+
+int tc_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            n = kNumSMs;
+        }
+    }
+    return n;
 }
 
 struct TcWorkspace {       // byte offsets into the caller's workspace (all 1 KB aligned)
@@ -363,7 +303,7 @@ bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels) {
     if (B < 1 || 2 * (long long)B > 0x7fffffff) return false;
     int h = H, w = W;
     for (int l = 0; l < levels; ++l) { if (h < 1 || w < 1) return false; h /= 2; w /= 2; }
-    return encode_fn() != nullptr;
+    return tc_encode_fn() != nullptr;
 }
 
 int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels) {
@@ -371,15 +311,15 @@ int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels) 
     return tc_workspace(B, C, H, W, levels).total;
 }
 
-static int split_transpose(const float* src, __nv_bfloat16* dst, int B, int C, int n, cudaStream_t s) {
+static int split_transpose(const float* src, __nv_bfloat16* dst, int B, int C, int n, float scale, cudaStream_t s) {
     dim3 grid(ceil_div(n, 32), ceil_div(C, 32), B);
-    split_transpose_kernel<<<grid, 256, 0, s>>>(src, dst, B, C, n);
+    split_transpose_kernel<<<grid, 256, 0, s>>>(src, dst, B, C, n, scale);
     return after_launch();
 }
 
 int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyramid, void* ws, int64_t ws_bytes,
                             int B, int C, int H, int W, int levels, cudaStream_t s) {
-    EncodeTiledFn enc = encode_fn();
+    EncodeTiledFn enc = tc_encode_fn();
     if (!enc) return PCFA_E_NODEVICE;
     const TcWorkspace wl = tc_workspace(B, C, H, W, levels);
     if (!ws || ws_bytes < wl.total || (reinterpret_cast<uintptr_t>(ws) & 15)) return PCFA_E_WORKSPACE;
@@ -388,7 +328,7 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
 
     // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
-    PCFA_TRY(split_transpose(fmap1, reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split), B, C, N, s));
+    PCFA_TRY(split_transpose(fmap1, reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split), B, C, N, 1.0f / sqrtf((float)C), s));
     const float* prev = fmap2;
     for (int l = 0; l < levels; ++l) {
         const float* cur = prev;
@@ -401,7 +341,7 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
             PCFA_TRY(after_launch());
             cur = pooled;
         }
-        PCFA_TRY(split_transpose(cur, reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]), B, C, L.h[l] * L.w[l], s));
+        PCFA_TRY(split_transpose(cur, reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]), B, C, L.h[l] * L.w[l], 1.0f, s));
         prev = cur;
     }
 
@@ -445,13 +385,7 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
         PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        PCFA_CUDA_TRY(cudaGetDevice(&dev));
-        PCFA_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    int grid = num_sms;
+    int grid = tc_num_sms();
     if ((long long)grid > P.total_tiles) grid = (int)P.total_tiles;
     corr_pyramid_tc_kernel<<<grid, TC_THREADS, smem, s>>>(maps, P, pyramid);
     return after_launch();

@@ -313,3 +313,37 @@ def test_allpairs_tcgen05_vs_oracle_small():
     f2 = g.standard_normal((1, 64, 12, 20)).astype(np.float32)
     tc, _ = _build_pyramid(cu(f1), cu(f2), 4, 2)
     assert_close(npy(tc), O.corr_pyramid_forward(f1, f2, 4), what="tcgen05 pyramid vs oracle", **TIGHT)
+
+
+def _pyramid_backward(gp, f1, f2, levels, impl):
+    from pcfa_b200 import _lib
+    lib = _lib.load()
+    B, C, H, W = f1.shape
+    g1, g2 = torch.full_like(f1, float("nan")), torch.full_like(f2, float("nan"))
+    wsb = lib.pcfa_corr_pyramid_workspace_bytes(B, C, H, W, levels)
+    wsp = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.pcfa_corr_pyramid_backward(_lib.ptr(gp), _lib.ptr(f1), _lib.ptr(f2), _lib.ptr(g1), _lib.ptr(g2),
+                                              _lib.ptr(wsp), wsb, B, C, H, W, levels, impl, _lib.stream()), "pyramid bwd")
+    torch.cuda.synchronize()
+    return g1, g2
+
+
+@pytest.mark.parametrize("shape,levels", [((1, 64, 16, 32), 4), ((2, 128, 16, 24), 3), ((1, 256, 12, 20), 2),
+                                          ((1, 256, 55, 128), 4), ((2, 256, 46, 64), 4), ((1, 48, 8, 8), 1)])
+def test_allpairs_backward_tcgen05_matches_fp32_simt(shape, levels):
+    """TF32 tensor-core backward (K-major pass I, MN-major pass II) vs the exact-fp32 SIMT backward.
+    Expected error: 2^-11 relative truncation of the gradient pyramid, random over the contraction."""
+    from pcfa_b200.corr_block import pyramid_layout
+    g = torch.Generator().manual_seed(sum(shape) + levels)
+    B, C, H, W = shape
+    f1 = torch.randn(shape, generator=g).cuda()
+    f2 = torch.randn(shape, generator=g).cuda()
+    offs, _, _ = pyramid_layout(B, H, W, levels)
+    gp = torch.randn(offs[-1], generator=g).cuda()
+    t1, t2 = _pyramid_backward(gp, f1, f2, levels, 2)
+    s1, s2 = _pyramid_backward(gp, f1, f2, levels, 1)
+    for name, a, b in (("grad_fmap1", t1, s1), ("grad_fmap2", t2, s2)):
+        assert torch.isfinite(a).all(), f"{name}: unwritten cells"
+        rel = float((a - b).norm() / b.norm())
+        mx = float((a - b).abs().max() / b.pow(2).mean().sqrt())
+        assert rel < 1e-3 and mx < 6e-3, f"{name}: rel L2 {rel:.2e}, max/rms {mx:.2e}"
