@@ -204,12 +204,55 @@ def golden_raft():
                         g_img1=_np(i1.grad), g_img2=_np(i2.grad))
 
 
+def golden_attack():
+    """The reference's pcfa_attack (attack_PCFA.py:40-294) end to end on CPU: RAFT with name-keyed weights,
+    one synthetic 128x160 pair, disjoint + change_of_variables, zero target, 3 outer L-BFGS steps."""
+    import tempfile
+    import attack_PCFA
+    from helper_functions import ownutilities, parsing_file
+    from helper_functions.own_models import ScaledInputModel
+    from models.raft.raft import RAFT
+    sys.path.insert(0, str(REPO))
+    from pcfa_b200.networks.weights import deterministic_state_, synthetic_pair
+    cfg = json.load(open(REF / "models/_config/raft_config.json"))
+
+    def fake_import_and_load(net='RAFT', make_unit_input=False, variable_change=False, device=None,
+                             make_scaled_input_model=False, **kw):
+        m = torch.nn.DataParallel(RAFT(dict(cfg)))            # ownutilities.py:105
+        deterministic_state_(m, seed=0, strip_prefix="module.")
+        return m
+    real = ownutilities.import_and_load
+    ownutilities.import_and_load = fake_import_and_load
+    try:
+        out = {}
+        for name, extra in (("dd_cov", []), ("cd_clip", ["--joint_perturbation", "--boxconstraint", "clipping"])):
+            args = parsing_file.create_parser('training', 'pcfa').parse_args(
+                ["--net", "RAFT", "--steps", "3", "--no_save", "--delta_bound", "0.005"] + extra)
+            cov = args.boxconstraint == "change_of_variables"
+            model = ScaledInputModel("RAFT", make_unit_input=True, variable_change=cov, eps_box=1e-7)
+            model.eval()
+            for p in model.parameters():
+                p.requires_grad = False
+            i1, i2 = synthetic_pair(0, 128, 160)
+            with tempfile.TemporaryDirectory() as tmp:
+                r = attack_PCFA.pcfa_attack(model, i1, i2, torch.zeros(1, 2, 128, 160), 0, tmp, 1e-7, torch.device("cpu"),
+                                            False, 2500. / 0.005, args)
+            keys = ("aee_gt", "aee_tgt", "aee_gt_tgt", "aee_adv_gt", "aee_adv_tgt", "aee_adv_pred", "l2_delta1", "l2_delta2",
+                    "l2_delta12", "aee_adv_tgt_min", "aee_adv_pred_min", "l2_delta12_min")
+            out[name] = {k: (None if v is None else float(v)) for k, v in zip(keys, r)}
+            print(name, out[name])
+        (OUT / "attack_raft.json").write_text(json.dumps(out, indent=1))
+    finally:
+        ownutilities.import_and_load = real
+        torch.autograd.set_detect_anomaly(False)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     _shim_reference()
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft):
+    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft, golden_attack):
         fn()
         print("wrote", fn.__name__)
 

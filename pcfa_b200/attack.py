@@ -22,7 +22,8 @@ from dataclasses import dataclass, field
 import torch
 
 from . import objective as J
-from .adapter import build_network, compute_flow, model_takes_unit_input, preprocess_img
+from .adapter import compute_flow, model_takes_unit_input, preprocess_img
+from .dist import pack_reduce_unpack
 
 
 def resolve_mu(mu: float, delta_bound: float, target: str) -> float:
@@ -242,22 +243,11 @@ class UniversalAttack:
         d2 = None if self.delta2 is None else self.delta2.detach()
         ev = GraphedEvaluate(fo, d1, d2, use_graph=self.use_graph)
         dist = self._dist()
-        n1 = d1.numel()
-
         def closure():
             self.closure_evals += 1
             loss_t = ev()
             if dist is not None:
-                self.flat[:n1].copy_(ev.g1.view(-1))
-                if d2 is not None:
-                    self.flat[n1:-1].copy_(ev.g2.view(-1))
-                self.flat[-1:].copy_(loss_t.view(1))
-                dist.all_reduce(self.flat)
-                self.flat.div_(dist.get_world_size())
-                ev.g1.view(-1).copy_(self.flat[:n1])
-                if d2 is not None:
-                    ev.g2.view(-1).copy_(self.flat[n1:-1])
-                loss_t = self.flat[-1]
+                loss_t = pack_reduce_unpack(self.flat, loss_t, ev.g1, ev.g2)
             self.delta1.grad = ev.g1
             if self.delta2 is not None:
                 self.delta2.grad = ev.g2
