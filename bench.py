@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=3)
     ap.add_argument("--channels-last", action="store_true", help="run the network's convolutions in NHWC memory format")
-    ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN autotune convolution algorithms during warm-up")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="disable cuDNN autotuning of the convolution algorithms during warm-up")
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--width", type=int, default=W_IMG)
     return ap.parse_args()
@@ -149,7 +149,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
 
-    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     net, i1_host, i2_host = make_problem(device, rank, args.height, args.width)
     if args.channels_last:
         net = net.to(memory_format=torch.channels_last)

@@ -219,15 +219,22 @@ def golden_attack():
     def fake_import_and_load(net='RAFT', make_unit_input=False, variable_change=False, device=None,
                              make_scaled_input_model=False, **kw):
         m = torch.nn.DataParallel(RAFT(dict(cfg)))            # ownutilities.py:105
-        deterministic_state_(m, seed=0, strip_prefix="module.")
+        deterministic_state_(m, seed=0, strip_prefix="module.", gain=GAIN[0])
         return m
     real = ownutilities.import_and_load
     ownutilities.import_and_load = fake_import_and_load
+    GAIN = [1.0]
     try:
         out = {}
-        for name, extra in (("dd_cov", []), ("cd_clip", ["--joint_perturbation", "--boxconstraint", "clipping"])):
+        cases = [("dd_cov", [], 1.0, 3), ("cd_clip", ["--joint_perturbation", "--boxconstraint", "clipping"], 1.0, 3)]
+        for st in (1, 2, 3):      # damped weights (flows of a few px): the well-conditioned parity cases
+            cases.append(("dd_cov_g05_s%d" % st, [], 0.5, st))
+        cases.append(("cd_clip_g05_s3", ["--joint_perturbation", "--boxconstraint", "clipping"], 0.5, 3))
+        cases.append(("dd_clip_mse_neg_g05_s2", ["--boxconstraint", "clipping", "--loss", "mse", "--target", "neg_flow"], 0.5, 2))
+        for name, extra, gain, steps in cases:
+            GAIN[0] = gain
             args = parsing_file.create_parser('training', 'pcfa').parse_args(
-                ["--net", "RAFT", "--steps", "3", "--no_save", "--delta_bound", "0.005"] + extra)
+                ["--net", "RAFT", "--steps", str(steps), "--no_save", "--delta_bound", "0.005"] + extra)
             cov = args.boxconstraint == "change_of_variables"
             model = ScaledInputModel("RAFT", make_unit_input=True, variable_change=cov, eps_box=1e-7)
             model.eval()
@@ -235,8 +242,9 @@ def golden_attack():
                 p.requires_grad = False
             i1, i2 = synthetic_pair(0, 128, 160)
             with tempfile.TemporaryDirectory() as tmp:
+                mu = 2500. / 0.005 * (1.0 if args.target == "zero" else 1.5)
                 r = attack_PCFA.pcfa_attack(model, i1, i2, torch.zeros(1, 2, 128, 160), 0, tmp, 1e-7, torch.device("cpu"),
-                                            False, 2500. / 0.005, args)
+                                            False, mu, args)
             keys = ("aee_gt", "aee_tgt", "aee_gt_tgt", "aee_adv_gt", "aee_adv_tgt", "aee_adv_pred", "l2_delta1", "l2_delta2",
                     "l2_delta12", "aee_adv_tgt_min", "aee_adv_pred_min", "l2_delta12_min")
             out[name] = {k: (None if v is None else float(v)) for k, v in zip(keys, r)}

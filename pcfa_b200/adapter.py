@@ -89,7 +89,7 @@ def compute_flow(model, network, x1, x2, test_mode=True, **kwargs):
     return model(x1, x2, **kwargs)
 
 
-def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = None, ops=None):
+def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = None, ops=None, gain: float = 1.0):
     """Construct a flow network with this package's operators (or `ops`, used by the tests to inject
     the oracle), weights from `weights` (a checkpoint path) or deterministic synthetic values."""
     from .networks.weights import deterministic_state_
@@ -111,7 +111,7 @@ def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = 
         sd = torch.load(weights, map_location="cpu")
         model.load_state_dict(sd.get("state_dict", sd) if isinstance(sd, dict) else sd)
     else:
-        deterministic_state_(model, seed)
+        deterministic_state_(model, seed, gain=gain)
     model = model.to(device).eval()
     for p in model.parameters():
         p.requires_grad = False

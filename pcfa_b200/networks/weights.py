@@ -3,7 +3,8 @@
 Every tensor of a state_dict is filled from a generator seeded by crc32(key) ^ seed, so two
 implementations of the same architecture (this package's and the reference's) receive bit-identical
 weights as long as their state_dict keys and shapes agree — which is also the checkpoint-compatibility
-contract.  Scales follow He initialisation so activations stay O(1) through the stack.
+contract.  Scales follow He initialisation so activations stay O(1) through the stack; `gain` < 1 damps
+the stack (gain 0.5 gives RAFT flows of a few pixels, like a trained network, instead of ~100 px).
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ import zlib
 import torch
 
 
-def deterministic_state_(model: torch.nn.Module, seed: int = 0, strip_prefix: str = "") -> torch.nn.Module:
+def deterministic_state_(model: torch.nn.Module, seed: int = 0, strip_prefix: str = "", gain: float = 1.0) -> torch.nn.Module:
     sd = model.state_dict()
     with torch.no_grad():
         for key in sorted(sd.keys()):
@@ -28,7 +29,7 @@ def deterministic_state_(model: torch.nn.Module, seed: int = 0, strip_prefix: st
                 v = 0.1 * torch.randn(t.shape, generator=g)
             elif t.dim() >= 2:
                 fan_in = t[0].numel()
-                v = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
+                v = torch.randn(t.shape, generator=g) * (gain * math.sqrt(2.0 / fan_in))
             elif name.endswith("weight"):
                 v = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
             else:
