@@ -204,6 +204,44 @@ def golden_raft():
                         g_img1=_np(i1.grad), g_img2=_np(i2.grad))
 
 
+def golden_networks():
+    """Reference GMA / PWCNet / FlowNet2 forward (and PWCNet backward) with name-keyed weights.  FlowNet2's three
+    CUDA-only extension modules are replaced by the oracle's operator classes (they cannot execute on CPU)."""
+    from argparse import Namespace
+    sys.path.insert(0, str(REPO))
+    from oracle import torch_ref as TR
+    from pcfa_b200.networks.weights import deterministic_state_, synthetic_pair
+    blob = {}
+    from models.gma.network import RAFTGMA
+    cfg = json.load(open(REF / "models/_config/gma_config.json"))
+    net = deterministic_state_(RAFTGMA(Namespace(**cfg)), 0, gain=0.5).eval()
+    i1, i2 = synthetic_pair(3, 128, 136)
+    with torch.no_grad():
+        blob["gma_flow"] = _np(net(i1, i2, iters=6, test_mode=True)[1])
+    from models.PWCNet.PWCNet import PWCDCNet
+    net = deterministic_state_(PWCDCNet(), 0).eval()
+    i1, i2 = synthetic_pair(4, 128, 192)
+    a = (i1 / 255.).requires_grad_(True)
+    flow = net(a, i2 / 255.)
+    go = torch.randn(flow.shape, generator=torch.Generator().manual_seed(16)) / flow.numel()
+    (flow * go).sum().backward()
+    blob.update(pwc_flow=_np(flow), pwc_gout=_np(go), pwc_g_img1=_np(a.grad))
+    for pkg, mod, name in (("correlation_package", "correlation", "Correlation"), ("resample2d_package", "resample2d", "Resample2d"),
+                           ("channelnorm_package", "channelnorm", "ChannelNorm")):
+        m = types.ModuleType(f"models.FlowNet.{pkg}.{mod}")
+        setattr(m, name, getattr(TR, name))
+        pk = types.ModuleType(f"models.FlowNet.{pkg}")
+        pk.__path__ = []
+        setattr(pk, mod, m)
+        sys.modules[f"models.FlowNet.{pkg}"], sys.modules[f"models.FlowNet.{pkg}.{mod}"] = pk, m
+    from models.FlowNet.FlowNet2 import FlowNet2
+    net = deterministic_state_(FlowNet2(Namespace(fp16=False, rgb_max=255.0), div_flow=20, batchNorm=False), 0, gain=0.7).eval()
+    i1, i2 = synthetic_pair(5, 64, 128)
+    with torch.no_grad():
+        blob["fn2_flow"] = _np(net(torch.stack((i1, i2), dim=-3)))
+    np.savez_compressed(OUT / "networks.npz", **blob)
+
+
 def golden_attack():
     """The reference's pcfa_attack (attack_PCFA.py:40-294) end to end on CPU: RAFT with name-keyed weights,
     one synthetic 128x160 pair, disjoint + change_of_variables, zero target, 3 outer L-BFGS steps."""
@@ -260,7 +298,7 @@ def main():
     _shim_reference()
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft, golden_attack):
+    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft, golden_networks, golden_attack):
         fn()
         print("wrote", fn.__name__)
 

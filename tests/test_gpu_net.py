@@ -127,3 +127,48 @@ def test_closure_is_cuda_graph_capturable(fp32_convs):
     graph.replay()
     torch.cuda.synchronize()
     assert abs(float(fo.terms[0]) - eager[0]) > 0
+
+
+@pytest.mark.parametrize("name,shape,gain,kw", [("GMA", (128, 136), 0.5, {}), ("PWCNet", (128, 192), 1.0, {}),
+                                                ("FlowNet2", (64, 128), 0.7, {})])
+def test_other_networks_gpu_match_reference_flows(golden, fp32_convs, name, shape, gain, kw):
+    """GMA / PWCNet / FlowNet2 with the CUDA operators against the reference networks' CPU flows
+    (tests/golden/networks.npz) and, for gradients, against the oracle's torch ops on the same GPU."""
+    from oracle import torch_ref as TR
+    from pcfa_b200.adapter import build_network, compute_flow
+    from pcfa_b200.networks.weights import synthetic_pair
+    z = golden("networks")
+    idx = {"GMA": 3, "PWCNet": 4, "FlowNet2": 5}[name]
+    key = {"GMA": "gma_flow", "PWCNet": "pwc_flow", "FlowNet2": "fn2_flow"}[name]
+    scale = 255. if name == "PWCNet" else 1.
+    res = {}
+    for tag, ops in (("cuda", None), ("torch", TR)):
+        if tag == "torch" and name == "FlowNet2":
+            continue                                       # the oracle's FlowNet2 ops are CPU-only (C)
+        net = build_network(name, device="cuda", seed=0, ops=ops, gain=gain)
+        if name == "GMA":
+            net.args["mixed_precision"] = False            # compare in fp32 (the reference CPU run cannot autocast)
+        i1, i2 = synthetic_pair(idx, *shape)
+        a, b = (i1 / scale).cuda().requires_grad_(True), (i2 / scale).cuda()
+        flow = compute_flow(net, name, a, b)
+        g = torch.randn(flow.shape, generator=torch.Generator().manual_seed(16)).cuda() / flow.numel()
+        (flow * g).sum().backward()
+        res[tag] = (flow.detach().cpu().numpy(), a.grad.cpu().numpy())
+    assert_close(res["cuda"][0], z[key], rtol=1e-3, atol_rms=2e-3, what=f"{name} flow vs reference (CPU)")
+    if "torch" in res:
+        assert_close(res["cuda"][0], res["torch"][0], rtol=1e-3, atol_rms=1e-3, what=f"{name} flow vs torch ops (GPU)")
+        assert _rel_l2(res["cuda"][1], res["torch"][1]) < 2e-2, _rel_l2(res["cuda"][1], res["torch"][1])
+    assert np.isfinite(res["cuda"][1]).all() and np.abs(res["cuda"][1]).sum() > 0
+
+
+def test_gma_autocast_config_runs(fp32_convs):
+    """GMA's shipped config enables fp16 autocast (models/_config/gma_config.json:5): the CorrBlock gets fp32."""
+    from pcfa_b200.adapter import build_network, compute_flow
+    from pcfa_b200.networks.weights import synthetic_pair
+    net = build_network("GMA", device="cuda", seed=0, gain=0.5)
+    assert net.args["mixed_precision"]
+    i1, i2 = synthetic_pair(3, 128, 136)
+    a = i1.cuda().requires_grad_(True)
+    flow = compute_flow(net, "GMA", a, i2.cuda())
+    flow.float().abs().mean().backward()
+    assert flow.shape == (1, 2, 128, 136) and torch.isfinite(a.grad).all()
