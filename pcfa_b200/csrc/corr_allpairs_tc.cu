@@ -237,6 +237,65 @@ split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict_
     }
 }
 
+// Fused operand prep for the target side: one pass over fmap2 produces the channel-last bf16 hi/mid planes of
+// pool_l(fmap2) for every level (successive 2x2 floor pooling, as F.avg_pool2d applied level by level).
+// CTA = 32 channels x (8 rows x 32 cols) of level 0: coalesced 128-byte row reads, 64-byte channel runs out.
+struct TcPrepArgs {
+    __nv_bfloat16* dst[TC_MAX_LEVELS];     // hi plane base per level; mid plane at + plane[l]
+    long long plane[TC_MAX_LEVELS];        // B * H_l * W_l * C
+    int h[TC_MAX_LEVELS], w[TC_MAX_LEVELS];
+    int levels, B, C;
+};
+__global__ void __launch_bounds__(256)
+prep_targets_kernel(const float* __restrict__ src, TcPrepArgs a) {
+    __shared__ float t0[32][8][33];     // [c][y][x] level 0 (padded)
+    __shared__ float t1[32][4][17];
+    __shared__ float t2[32][2][9];
+    __shared__ float t3[32][1][5];
+    const int H = a.h[0], W = a.w[0];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int cblocks = a.C / 32;
+    const int b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    for (int c = 0; c < 32; ++c) {
+        const int y = y0 + ty, x = x0 + tx;
+        t0[c][ty][tx] = (y < H && x < W) ? __ldg(src + (((long long)b * a.C + c0 + c) * H + y) * W + x) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
+        const int c = e / 64, r = (e / 16) % 4, q = e % 16;
+        t1[c][r][q] = 0.25f * ((t0[c][2 * r][2 * q] + t0[c][2 * r][2 * q + 1]) + (t0[c][2 * r + 1][2 * q] + t0[c][2 * r + 1][2 * q + 1]));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 2 * 8; e += 256) {
+        const int c = e / 16, r = (e / 8) % 2, q = e % 8;
+        t2[c][r][q] = 0.25f * ((t1[c][2 * r][2 * q] + t1[c][2 * r][2 * q + 1]) + (t1[c][2 * r + 1][2 * q] + t1[c][2 * r + 1][2 * q + 1]));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 * 4) {
+        const int c = threadIdx.x / 4, q = threadIdx.x % 4;
+        t3[c][0][q] = 0.25f * ((t2[c][0][2 * q] + t2[c][0][2 * q + 1]) + (t2[c][1][2 * q] + t2[c][1][2 * q + 1]));
+    }
+    __syncthreads();
+    // write: lane = channel (contiguous in the channel-last layout), loop over the cells of each level
+    const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    for (int l = 0; l < a.levels; ++l) {
+        const int hh = 8 >> l, ww = 32 >> l;
+        const int Hl = a.h[l], Wl = a.w[l];
+        for (int cell = slot; cell < hh * ww; cell += 8) {
+            const int r = cell / ww, q = cell % ww;
+            const int y = (y0 >> l) + r, x = (x0 >> l) + q;
+            if (y >= Hl || x >= Wl) continue;
+            const float v = (l == 0) ? t0[c][r][q] : (l == 1) ? t1[c][r][q] : (l == 2) ? t2[c][r][q] : t3[c][r][q];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const long long o = (((long long)b * Hl + y) * Wl + x) * a.C + c0 + c;
+            a.dst[l][o] = hi;
+            a.dst[l][a.plane[l] + o] = mid;
+        }
+    }
+}
+
 __global__ void tc_avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int Hi,
                                    int Wi, int Ho, int Wo) {
     const long long total = R * Ho * Wo;
@@ -329,20 +388,17 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
 
     // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
     PCFA_TRY(split_transpose(fmap1, reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split), B, C, N, 1.0f / sqrtf((float)C), s));
-    const float* prev = fmap2;
-    for (int l = 0; l < levels; ++l) {
-        const float* cur = prev;
-        if (l > 0) {
-            float* pooled = reinterpret_cast<float*>(wsb + wl.pooled[l]);
-            const long long cnt = (long long)B * C * L.h[l] * L.w[l];
-            int blocks = (int)((cnt + 255) / 256);
-            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-            tc_avgpool2_kernel<<<blocks, 256, 0, s>>>(prev, pooled, (long long)B * C, L.h[l - 1], L.w[l - 1], L.h[l], L.w[l]);
-            PCFA_TRY(after_launch());
-            cur = pooled;
+    {
+        TcPrepArgs pa{};
+        pa.levels = levels; pa.B = B; pa.C = C;
+        for (int l = 0; l < levels; ++l) {
+            pa.dst[l] = reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]);
+            pa.plane[l] = (long long)B * L.h[l] * L.w[l] * C;
+            pa.h[l] = L.h[l]; pa.w[l] = L.w[l];
         }
-        PCFA_TRY(split_transpose(cur, reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]), B, C, L.h[l] * L.w[l], 1.0f, s));
-        prev = cur;
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * (C / 32));
+        prep_targets_kernel<<<grid, 256, 0, s>>>(fmap2, pa);
+        PCFA_TRY(after_launch());
     }
 
     // ---- tensor maps

@@ -35,11 +35,14 @@ __device__ __forceinline__ LookupGeom lookup_geom(float cx, float cy, int level,
     return g;
 }
 
-// grid: (ceil(N/QB) * B, levels)
+// grid: (ceil(N/QB) * B, levels).  RT > 0: radius known at compile time (all index divisions become
+// multiply-shift; the runtime-radius instantiation spent most of its issue slots on integer division).
+template <int RT>
 __global__ void __launch_bounds__(LOOKUP_THREADS)
 corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restrict__ coords,
-                       float* __restrict__ out, PyramidLayout L, int B, int H, int W, int r) {
+                       float* __restrict__ out, PyramidLayout L, int B, int H, int W, int r_rt) {
     extern __shared__ float smem[];
+    const int r = RT > 0 ? RT : r_rt;
     const int D = 2 * r + 1, F = D + 1, FP = F * F;
     const int FS = FP | 1;                       // odd stride → conflict-free lane==query reads
     float*      S    = smem;                     // [QB][FS]
@@ -94,10 +97,12 @@ corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restric
 // grid: (ceil(N/QB) * B, levels).  Every (q, l, cell) address is touched by exactly one thread of
 // one CTA per launch, so the accumulation is race-free within a launch; RED (no return) is used
 // because successive lookups of one forward pass accumulate into the same buffer in stream order.
+template <int RT>
 __global__ void __launch_bounds__(LOOKUP_THREADS)
 corr_lookup_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ coords,
-                       float* __restrict__ gpyr, PyramidLayout L, int B, int H, int W, int r) {
+                       float* __restrict__ gpyr, PyramidLayout L, int B, int H, int W, int r_rt) {
     extern __shared__ float smem[];
+    const int r = RT > 0 ? RT : r_rt;
     const int D = 2 * r + 1, F = D + 1, FP = F * F, nch = D * D;
     const int GS = nch | 1;                      // odd stride
     float*      G    = smem;                     // [QB][GS]  gout of this (group, level)
@@ -168,11 +173,14 @@ extern "C" int pcfa_corr_lookup_forward(const float* pyramid, const float* coord
     const int D = 2 * radius + 1, FP = (D + 1) * (D + 1);
     const size_t smem = (size_t)QB * (FP | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);
-    if (smem > 48 * 1024)
-        PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_fwd_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_lookup_fwd_kernel<<<grid, LOOKUP_THREADS, smem, as_stream(stream)>>>(pyramid, coords, out, L,
-                                                                              B, H, W, radius);
+    cudaStream_t s = as_stream(stream);
+    if (radius == 4)      corr_lookup_fwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
+    else if (radius == 3) corr_lookup_fwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
+    else {
+        if (smem > 48 * 1024)
+            PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        corr_lookup_fwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
+    }
     return after_launch();
 }
 
@@ -184,11 +192,13 @@ extern "C" int pcfa_corr_lookup_backward(const float* grad_out, const float* coo
     const int D = 2 * radius + 1;
     const size_t smem = (size_t)QB * ((D * D) | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);
-    if (smem > 48 * 1024)
-        PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_bwd_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_lookup_bwd_kernel<<<grid, LOOKUP_THREADS, smem, as_stream(stream)>>>(grad_out, coords,
-                                                                              grad_pyramid, L, B, H,
-                                                                              W, radius);
+    cudaStream_t s = as_stream(stream);
+    if (radius == 4)      corr_lookup_bwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
+    else if (radius == 3) corr_lookup_bwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
+    else {
+        if (smem > 48 * 1024)
+            PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        corr_lookup_bwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
+    }
     return after_launch();
 }
