@@ -18,7 +18,8 @@
 // in fp32, so the only rounding beyond fp32 is the 2^-11 relative truncation of G — the same
 // precision class as the cuDNN TF32 convolutions that produce and consume these gradients.
 // One CTA owns two 128-row blocks (two TMEM accumulators of C columns) so each streamed channel
-// chunk is used twice; the contraction range is split across CTAs (RED.ADD into zeroed outputs).
+// chunk is used twice; the linear (row-block pair, K-chunk) work space is cut into equal contiguous shares,
+// one per SM (a CTA finishes a block pair's partial sum with RED.ADD into zeroed outputs and moves on).
 #include "tc_common.cuh"
 #include <math.h>
 
@@ -34,12 +35,41 @@ struct BwMaps {
 };
 
 struct BwParams {
-    int B, C, N, levels, pass, splits, chunks_total, units_per_sample;
+    int B, C, N, levels, pass, chunks_total, units_per_sample;
+    long long work_total;                // B * units_per_sample * chunks_total  (linear (unit, K-chunk) space)
     int nl[BW_MAX_LEVELS];
     int chunk_off[BW_MAX_LEVELS + 1];    // pass I : K-chunk prefix over levels
     int unit_off[BW_MAX_LEVELS + 1];     // pass II: block-pair prefix over levels
     float* out[BW_MAX_LEVELS];           // pass I: out[0] = grad_fmap1 ; pass II: grad of P_l (out[0] = grad_fmap2)
 };
+
+struct BwSegment { int b, level, rows_total, m0a, m0b, nblk, k0, k1; long long next; };
+
+// The CTA's share [w, w_end) of the linear work space is cut at unit boundaries into segments; every warp role
+// walks the same segments.
+__device__ __forceinline__ BwSegment bw_segment(long long w, long long w_end, const BwParams& P) {
+    BwSegment sg;
+    const long long ug = w / P.chunks_total;                       // global unit index
+    sg.k0 = (int)(w - ug * P.chunks_total);
+    const long long unit_end = (ug + 1) * P.chunks_total;
+    sg.next = unit_end < w_end ? unit_end : w_end;
+    sg.k1 = sg.k0 + (int)(sg.next - w);
+    sg.b = (int)(ug / P.units_per_sample);
+    const int unit = (int)(ug - (long long)sg.b * P.units_per_sample);
+    int level = 0, pair = unit;
+    if (P.pass == 2) {
+#pragma unroll
+        for (int l = 1; l < BW_MAX_LEVELS; ++l)
+            if (l < P.levels && unit >= P.unit_off[l]) level = l;
+        pair = unit - P.unit_off[level];
+    }
+    sg.level = level;
+    sg.rows_total = (P.pass == 1) ? P.N : P.nl[level];
+    sg.m0a = pair * 2 * BW_BM;
+    sg.m0b = sg.m0a + BW_BM;
+    sg.nblk = (sg.m0b < sg.rows_total) ? 2 : 1;
+    return sg;
+}
 
 __global__ void __launch_bounds__(BW_THREADS, 1)
 corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P) {
@@ -48,33 +78,20 @@ corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P
     const uint32_t b_bytes = (uint32_t)P.C * 128u;                       // one [C x 32 tf32] tile
     const uint32_t stage_bytes = 2 * BW_A_BYTES + 2 * b_bytes;
     const uint32_t bars = base + BW_STAGES * stage_bytes;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW_STAGES, bar_done = bar_empty + 8 * BW_STAGES;
-    const uint32_t tmem_slot = bar_done + 8;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW_STAGES;
+    const uint32_t bar_accfull = bar_empty + 8 * BW_STAGES, bar_accempty = bar_accfull + 8;
+    const uint32_t tmem_slot = bar_accempty + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // ---- decode the work unit
-    const int split = blockIdx.x % P.splits;
-    const int rest = blockIdx.x / P.splits;
-    const int b = rest / P.units_per_sample;
-    const int unit = rest - b * P.units_per_sample;
-    int level = 0, pair = unit;
-    if (P.pass == 2) {
-#pragma unroll
-        for (int l = 1; l < BW_MAX_LEVELS; ++l)
-            if (l < P.levels && unit >= P.unit_off[l]) level = l;
-        pair = unit - P.unit_off[level];
-    }
-    const int rows_total = (P.pass == 1) ? P.N : P.nl[level];             // extent of the blocked (M) index
-    const int m0[2] = {pair * 2 * BW_BM, (pair * 2 + 1) * BW_BM};
-    const int nblk = (m0[1] < rows_total) ? 2 : 1;
-    const int k_begin = (int)((long long)P.chunks_total * split / P.splits);
-    const int k_end = (int)((long long)P.chunks_total * (split + 1) / P.splits);
+    const long long w_begin = P.work_total * blockIdx.x / gridDim.x;
+    const long long w_end = P.work_total * (blockIdx.x + 1) / gridDim.x;
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BW_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_done, 1);
+        mbar_init(bar_accfull, 1);
+        mbar_init(bar_accempty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -91,73 +108,96 @@ corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer
         int stage = 0; uint32_t phase = 0;
-        for (int kc = k_begin; kc < k_end; ++kc) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t dst = base + stage * stage_bytes;
-            const uint32_t full = bar_full + 8 * stage;
-            mbar_expect_tx(full, nblk * BW_A_BYTES + 2 * b_bytes);
-            if (P.pass == 1) {
-                int l = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw_segment(w, w_end, P);
+            for (int kc = sg.k0; kc < sg.k1; ++kc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t dst = base + stage * stage_bytes;
+                const uint32_t full = bar_full + 8 * stage;
+                mbar_expect_tx(full, sg.nblk * BW_A_BYTES + 2 * b_bytes);
+                if (P.pass == 1) {
+                    int l = 0;
 #pragma unroll
-                for (int i = 1; i < BW_MAX_LEVELS; ++i)
-                    if (i < P.levels && kc >= P.chunk_off[i]) l = i;
-                const int j0 = (kc - P.chunk_off[l]) * BW_BK;
-                for (int r = 0; r < nblk; ++r) tma_load_3d(dst + r * BW_A_BYTES, &maps.a[l], full, j0, m0[r], b);
-                tma_load_3d(dst + 2 * BW_A_BYTES, &maps.b[l], full, j0, 0, b);
-                tma_load_3d(dst + 2 * BW_A_BYTES + b_bytes, &maps.b[l], full, j0, 0, P.B + b);
-            } else {
-                const int i0 = kc * BW_BK;
-                for (int r = 0; r < nblk; ++r)
+                    for (int i = 1; i < BW_MAX_LEVELS; ++i)
+                        if (i < P.levels && kc >= P.chunk_off[i]) l = i;
+                    const int j0 = (kc - P.chunk_off[l]) * BW_BK;
+                    tma_load_3d(dst, &maps.a[l], full, j0, sg.m0a, sg.b);
+                    if (sg.nblk == 2) tma_load_3d(dst + BW_A_BYTES, &maps.a[l], full, j0, sg.m0b, sg.b);
+                    tma_load_3d(dst + 2 * BW_A_BYTES, &maps.b[l], full, j0, 0, sg.b);
+                    tma_load_3d(dst + 2 * BW_A_BYTES + b_bytes, &maps.b[l], full, j0, 0, P.B + sg.b);
+                } else {
+                    const int i0 = kc * BW_BK;
                     for (int g = 0; g < 4; ++g)
-                        tma_load_3d(dst + r * BW_A_BYTES + g * 4096, &maps.a[level], full, m0[r] + 32 * g, i0, b);
-                tma_load_3d(dst + 2 * BW_A_BYTES, &maps.b[0], full, i0, 0, b);
-                tma_load_3d(dst + 2 * BW_A_BYTES + b_bytes, &maps.b[0], full, i0, 0, P.B + b);
+                        tma_load_3d(dst + g * 4096, &maps.a[sg.level], full, sg.m0a + 32 * g, i0, sg.b);
+                    if (sg.nblk == 2)
+                        for (int g = 0; g < 4; ++g)
+                            tma_load_3d(dst + BW_A_BYTES + g * 4096, &maps.a[sg.level], full, sg.m0b + 32 * g, i0, sg.b);
+                    tma_load_3d(dst + 2 * BW_A_BYTES, &maps.b[0], full, i0, 0, sg.b);
+                    tma_load_3d(dst + 2 * BW_A_BYTES + b_bytes, &maps.b[0], full, i0, 0, P.B + sg.b);
+                }
+                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
+            w = sg.next;
         }
     } else if (warp == 1 && lane == 0) {
         // ===================================================================== MMA issuer
         // D[128 x C] (fp32, TMEM) += A[128 x 8] (tf32) * B[C x 8]^T ; A K-major (pass I) or MN-major (pass II)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((P.pass == 2 ? 1u : 0u) << 15) |
                                ((uint32_t)(P.C >> 3) << 17) | ((uint32_t)(BW_BM >> 4) << 24);
-        int stage = 0; uint32_t phase = 0;
-        for (int kc = k_begin; kc < k_end; ++kc) {
-            mbar_wait(bar_full + 8 * stage, phase);
+        int stage = 0; uint32_t phase = 0, accphase = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw_segment(w, w_end, P);
+            mbar_wait(bar_accempty, accphase ^ 1);            // epilogue has drained the previous segment
             tc_fence_after();
-            const uint32_t sa = base + stage * stage_bytes, sb_hi = sa + 2 * BW_A_BYTES, sb_lo = sb_hi + b_bytes;
-            for (int r = 0; r < nblk; ++r) {
-                const uint32_t d_tmem = tmem_base + r * P.C;
+            for (int kc = sg.k0; kc < sg.k1; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = base + stage * stage_bytes, sb_hi = sa + 2 * BW_A_BYTES, sb_lo = sb_hi + b_bytes;
+                for (int r = 0; r < sg.nblk; ++r) {
+                    const uint32_t d_tmem = tmem_base + r * P.C;
 #pragma unroll
-                for (int kk = 0; kk < BW_BK / 8; ++kk) {
-                    const uint64_t ad = (P.pass == 1) ? umma_desc_sw128(sa + r * BW_A_BYTES + kk * 32)
-                                                      : umma_desc_mn_tf32(sa + r * BW_A_BYTES + kk * 1024, 4096, 512);
-                    tc_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_hi + kk * 32), idesc, (kc != k_begin) || (kk != 0));
-                    tc_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_lo + kk * 32), idesc, 1);
+                    for (int kk = 0; kk < BW_BK / 8; ++kk) {
+                        const uint64_t ad = (P.pass == 1) ? umma_desc_sw128(sa + r * BW_A_BYTES + kk * 32)
+                                                          : umma_desc_mn_tf32(sa + r * BW_A_BYTES + kk * 1024, 4096, 512);
+                        tc_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_hi + kk * 32), idesc, (kc != sg.k0) || (kk != 0));
+                        tc_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_lo + kk * 32), idesc, 1);
+                    }
                 }
+                tc_commit(bar_empty + 8 * stage);
+                if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(bar_empty + 8 * stage);
-            if (++stage == BW_STAGES) { stage = 0; phase ^= 1; }
+            tc_commit(bar_accfull);
+            accphase ^= 1;
+            w = sg.next;
         }
-        tc_commit(bar_done);
     } else if (warp >= 4) {
-        // ===================================================================== epilogue (once)
+        // ===================================================================== epilogue (per segment)
         const int ew = warp & 3, r = (warp - 4) >> 2;            // TMEM lane group, accumulator block
-        if (r < nblk && k_end > k_begin) {
-            mbar_wait(bar_done, 0);
+        uint32_t accphase = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw_segment(w, w_end, P);
+            mbar_wait(bar_accfull, accphase);
             tc_fence_after();
-            const int m = m0[r] + ew * 32 + lane;                 // row of G's blocked index (query or cell)
-            float* out = P.out[(P.pass == 1) ? 0 : level] + (long long)b * P.C * rows_total + m;
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + r * P.C;
-            for (int c0 = 0; c0 < P.C; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr + c0, v);
-                tc_wait_ld();
-                if (m < rows_total) {
+            if (r < sg.nblk) {
+                const int m = (r == 0 ? sg.m0a : sg.m0b) + ew * 32 + lane;     // query (pass I) or cell (pass II)
+                float* out = P.out[(P.pass == 1) ? 0 : sg.level] + (long long)sg.b * P.C * sg.rows_total + m;
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + r * P.C;
+                for (int c0 = 0; c0 < P.C; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c0, v);
+                    tc_wait_ld();
+                    if (m < sg.rows_total) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < P.C) red_add(out + (long long)(c0 + j) * rows_total, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < P.C) red_add(out + (long long)(c0 + j) * sg.rows_total, __uint_as_float(v[j]));
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty);
+            accphase ^= 1;
+            w = sg.next;
         }
     }
     tc_fence_before();
@@ -178,6 +218,89 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
         const float hf = __uint_as_float(h);
         hi[i] = hf;
         lo[i] = v - hf;
+    }
+}
+
+// Fused backward prep, one launch: TF32 hi/lo planes of alpha*fmap1 and of alpha*pool_l(fmap2) for every level
+// (successive 2x2 floor pooling), and zero-fill of every RED.ADD target (grad_fmap1, grad_fmap2, grad P_l).
+// CTA = 32 channels x (8 rows x 32 cols) of level 0; blockIdx.z selects (which fmap, sample, channel block).
+struct BwPrepArgs {
+    float* f1_hi; long long f1_plane;                       // [2][B][C][N]
+    float* p_hi[BW_MAX_LEVELS]; long long p_plane[BW_MAX_LEVELS];   // [2][B][C][N_l]
+    float* zero1; float* zero2; float* zero_gp[BW_MAX_LEVELS];     // grad_fmap1, grad_fmap2, grad P_l (l >= 1)
+    int h[BW_MAX_LEVELS], w[BW_MAX_LEVELS];
+    int levels, B, C;
+    float alpha;
+};
+__device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    *hi = __uint_as_float(h);
+    *lo = v - *hi;
+}
+__global__ void __launch_bounds__(256)
+bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPrepArgs a) {
+    __shared__ float t0[32][8][33];
+    __shared__ float t1[32][4][17];
+    __shared__ float t2[32][2][9];
+    __shared__ float t3[32][1][5];
+    const int H = a.h[0], W = a.w[0];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int cblocks = ceil_div(a.C, 32);
+    const int which = blockIdx.z / (a.B * cblocks);                  // 0: fmap1, 1: fmap2
+    const int rem = blockIdx.z % (a.B * cblocks);
+    const int b = rem / cblocks, c0 = (rem % cblocks) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int y = y0 + ty, x = x0 + tx;
+    const bool inb = y < H && x < W;
+    const long long hw = (long long)H * W;
+    if (which == 0) {
+        for (int c = 0; c < 32 && c0 + c < a.C; ++c) {
+            if (!inb) continue;
+            const long long o = ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x;
+            float hi, lo;
+            tf32_split(__ldg(f1 + o) * a.alpha, &hi, &lo);
+            a.f1_hi[o] = hi;
+            a.f1_hi[a.f1_plane + o] = lo;
+            a.zero1[o] = 0.f;
+            a.zero2[o] = 0.f;
+        }
+        return;
+    }
+    for (int c = 0; c < 32; ++c)
+        t0[c][ty][tx] = (inb && c0 + c < a.C) ? __ldg(f2 + ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x) * a.alpha : 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
+        const int c = e / 64, r = (e / 16) % 4, q = e % 16;
+        t1[c][r][q] = 0.25f * ((t0[c][2 * r][2 * q] + t0[c][2 * r][2 * q + 1]) + (t0[c][2 * r + 1][2 * q] + t0[c][2 * r + 1][2 * q + 1]));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 2 * 8; e += 256) {
+        const int c = e / 16, r = (e / 8) % 2, q = e % 8;
+        t2[c][r][q] = 0.25f * ((t1[c][2 * r][2 * q] + t1[c][2 * r][2 * q + 1]) + (t1[c][2 * r + 1][2 * q] + t1[c][2 * r + 1][2 * q + 1]));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 * 4) {
+        const int c = threadIdx.x / 4, q = threadIdx.x % 4;
+        t3[c][0][q] = 0.25f * ((t2[c][0][2 * q] + t2[c][0][2 * q + 1]) + (t2[c][1][2 * q] + t2[c][1][2 * q + 1]));
+    }
+    __syncthreads();
+    for (int l = 0; l < a.levels; ++l) {
+        const int hh = 8 >> l, ww = 32 >> l, cells = hh * ww;
+        const int Hl = a.h[l], Wl = a.w[l];
+        for (int e = threadIdx.x; e < 32 * cells; e += 256) {
+            const int c = e / cells, cell = e - c * cells;
+            const int r = cell / ww, q = cell - r * ww;
+            const int yy = (y0 >> l) + r, xx = (x0 >> l) + q;
+            if (yy >= Hl || xx >= Wl || c0 + c >= a.C) continue;
+            const float v = (l == 0) ? t0[c][r][q] : (l == 1) ? t1[c][r][q] : (l == 2) ? t2[c][r][q] : t3[c][r][q];
+            const long long o = (((long long)b * a.C + c0 + c) * Hl + yy) * Wl + xx;
+            float hi, lo;
+            tf32_split(v, &hi, &lo);
+            a.p_hi[l][o] = hi;
+            a.p_hi[l][a.p_plane[l] + o] = lo;
+            if (l > 0) a.zero_gp[l][o] = 0.f;
+        }
     }
 }
 
@@ -274,33 +397,23 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
     const float alpha = 1.0f / sqrtf((float)C);
 
-    // ---- zero the RED.ADD targets
-    PCFA_CUDA_TRY(cudaMemsetAsync(gf1, 0, (size_t)B * C * N * 4, s));
-    PCFA_CUDA_TRY(cudaMemsetAsync(gf2, 0, (size_t)B * C * N * 4, s));
-    for (int l = 1; l < levels; ++l)
-        PCFA_CUDA_TRY(cudaMemsetAsync(wsb + wl.gp[l], 0, (size_t)B * C * L.h[l] * L.w[l] * 4, s));
-
-    // ---- operand prep: alpha * fmap1 and alpha * pool_l(fmap2), split into TF32 hi / lo planes
+    // ---- one launch: operand prep (alpha folded in, pooling, TF32 hi/lo split) + zero-fill of the RED.ADD targets
     {
-        const long long n = (long long)B * C * N;
-        float* hi = reinterpret_cast<float*>(wsb + wl.f1_split);
-        split_tf32_kernel<<<grid1(n), 256, 0, s>>>(f1, hi, hi + n, n, alpha);
-        PCFA_TRY(after_launch());
-    }
-    const float* prev = f2;
-    for (int l = 0; l < levels; ++l) {
-        const long long n = (long long)B * C * L.h[l] * L.w[l];
-        const float* cur = prev;
-        if (l > 0) {
-            float* pooled = reinterpret_cast<float*>(wsb + wl.pooled[l]);
-            bw_avgpool2_kernel<<<grid1(n), 256, 0, s>>>(prev, pooled, (long long)B * C, L.h[l - 1], L.w[l - 1], L.h[l], L.w[l]);
-            PCFA_TRY(after_launch());
-            cur = pooled;
+        BwPrepArgs pa{};
+        pa.levels = levels; pa.B = B; pa.C = C; pa.alpha = alpha;
+        pa.f1_hi = reinterpret_cast<float*>(wsb + wl.f1_split);
+        pa.f1_plane = (long long)B * C * N;
+        pa.zero1 = gf1; pa.zero2 = gf2;
+        for (int l = 0; l < levels; ++l) {
+            pa.p_hi[l] = reinterpret_cast<float*>(wsb + wl.p_split[l]);
+            pa.p_plane[l] = (long long)B * C * L.h[l] * L.w[l];
+            pa.zero_gp[l] = (l == 0) ? nullptr : reinterpret_cast<float*>(wsb + wl.gp[l]);
+            pa.h[l] = L.h[l]; pa.w[l] = L.w[l];
         }
-        float* hi = reinterpret_cast<float*>(wsb + wl.p_split[l]);
-        split_tf32_kernel<<<grid1(n), 256, 0, s>>>(cur, hi, hi + n, n, alpha);
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), 2 * B * ceil_div(C, 32));
+        if (grid.z > 65535) return PCFA_E_TOOLARGE;
+        bw_prep_kernel<<<grid, 256, 0, s>>>(f1, f2, pa);
         PCFA_TRY(after_launch());
-        prev = cur;
     }
 
     const int smem = BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
@@ -327,11 +440,10 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         for (int l = levels; l < BW_MAX_LEVELS; ++l) { maps.a[l] = maps.a[0]; maps.b[l] = maps.b[0]; }
         P.chunks_total = off;
         P.units_per_sample = ceil_div(ceil_div(N, BW_BM), 2);
-        const int units = B * P.units_per_sample;
-        P.splits = units >= sms ? 1 : sms / units;
-        if (P.splits > off) P.splits = off;
+        P.work_total = (long long)B * P.units_per_sample * P.chunks_total;
         P.out[0] = gf1;
-        corr_pyramid_bwd_tc_kernel<<<units * P.splits, BW_THREADS, smem, s>>>(maps, P);
+        const int grid = (int)(P.work_total < sms ? P.work_total : sms);
+        corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
         PCFA_TRY(after_launch());
     }
     // ---- pass II: grad of P_l (level 0 goes straight into grad_fmap2)
@@ -352,10 +464,9 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         for (int l = 1; l < BW_MAX_LEVELS; ++l) maps.b[l] = maps.b[0];
         P.chunks_total = ceil_div(N, BW_BK);
         P.units_per_sample = off;
-        const int units = B * off;
-        P.splits = units >= sms ? 1 : sms / units;
-        if (P.splits > P.chunks_total) P.splits = P.chunks_total;
-        corr_pyramid_bwd_tc_kernel<<<units * P.splits, BW_THREADS, smem, s>>>(maps, P);
+        P.work_total = (long long)B * off * P.chunks_total;
+        const int grid = (int)(P.work_total < sms ? P.work_total : sms);
+        corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
         PCFA_TRY(after_launch());
     }
     if (levels > 1) {

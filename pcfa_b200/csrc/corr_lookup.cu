@@ -64,20 +64,37 @@ corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restric
     }
     __syncthreads();
 
+    // gather: one warp per query, lanes walk the footprint cells (cell -> (row, col) is the same for every
+    // query, so it is computed once per thread; everything per query is warp-uniform)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* lvl = pyramid + L.off[l];
-    for (int e = threadIdx.x; e < nq * FP; e += LOOKUP_THREADS) {
-        const int qi = e / FP, cell = e - qi * FP;
-        const int rr = cell / F, cc = cell - rr * F;
+    const int64_t plane = (int64_t)Hl * Wl;
+    constexpr int kMaxPass = 8;                   // (2r+2)^2 <= 256 cells for r <= 7; larger radii loop more
+    const int npass = ceil_div(FP, 32);
+    for (int qi = warp; qi < nq; qi += LOOKUP_THREADS / 32) {
         const LookupGeom g = geom[qi];
-        const int y = g.iy0 + rr, x = g.ix0 + cc;
-        float v = 0.f;
-        if (y >= 0 && y < Hl && x >= 0 && x < Wl)
-            v = __ldg(lvl + ((int64_t)b * N + q0 + qi) * ((int64_t)Hl * Wl) + (int64_t)y * Wl + x);
-        S[qi * FS + cell] = v;
+        const float* src = lvl + ((int64_t)b * N + q0 + qi) * plane;
+        float* dstq = S + qi * FS;
+#pragma unroll
+        for (int ps = 0; ps < kMaxPass; ++ps) {
+            if (ps >= npass) break;
+            const int cell = ps * 32 + lane;
+            const int rr = cell / F, cc = cell - rr * F;
+            const int y = g.iy0 + rr, x = g.ix0 + cc;
+            if (cell < FP) {
+                float v = 0.f;
+                if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl) v = __ldg(src + y * Wl + x);
+                dstq[cell] = v;
+            }
+        }
+        for (int cell = kMaxPass * 32 + lane; cell < FP; cell += 32) {     // r > 7 only
+            const int rr = cell / F, cc = cell - rr * F;
+            const int y = g.iy0 + rr, x = g.ix0 + cc;
+            dstq[cell] = ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl) ? __ldg(src + y * Wl + x) : 0.f;
+        }
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane < nq) {
         const LookupGeom g = geom[lane];
         const float w00 = (1.f - g.fx) * (1.f - g.fy), w01 = g.fx * (1.f - g.fy);
@@ -130,25 +147,28 @@ corr_lookup_bwd_kernel(const float* __restrict__ gout, const float* __restrict__
     }
     __syncthreads();
 
+    // scatter: one warp per query, lanes = footprint cells (adjoint gather of <= 4 taps per cell)
     float* lvl = gpyr + L.off[l];
-    for (int e = threadIdx.x; e < nq * FP; e += LOOKUP_THREADS) {
-        const int qi = e / FP, cell = e - qi * FP;
-        const int rr = cell / F, cc = cell - rr * F;
+    const int64_t plane = (int64_t)Hl * Wl;
+    for (int qi = warp; qi < nq; qi += LOOKUP_THREADS / 32) {
         const LookupGeom g = geom[qi];
-        const int y = g.iy0 + rr, x = g.ix0 + cc;
-        if (y < 0 || y >= Hl || x < 0 || x >= Wl) continue;
-        // cell (rr,cc) receives: tap (a=cc,  b=rr)   * (1-fx)(1-fy)
-        //                        tap (a=cc-1,b=rr)   * fx(1-fy)
-        //                        tap (a=cc,  b=rr-1) * (1-fx)fy
-        //                        tap (a=cc-1,b=rr-1) * fx*fy
+        float* dst = lvl + ((int64_t)b * N + q0 + qi) * plane;
         const float* Gq = G + qi * GS;
-        const bool a0 = cc < D, a1 = cc > 0, b0 = rr < D, b1 = rr > 0;
-        float acc = 0.f;
-        if (a0 && b0) acc += (1.f - g.fx) * (1.f - g.fy) * Gq[cc * D + rr];
-        if (a1 && b0) acc += g.fx * (1.f - g.fy) * Gq[(cc - 1) * D + rr];
-        if (a0 && b1) acc += (1.f - g.fx) * g.fy * Gq[cc * D + rr - 1];
-        if (a1 && b1) acc += g.fx * g.fy * Gq[(cc - 1) * D + rr - 1];
-        red_add(lvl + ((int64_t)b * N + q0 + qi) * ((int64_t)Hl * Wl) + (int64_t)y * Wl + x, acc);
+        const float w00 = (1.f - g.fx) * (1.f - g.fy), w01 = g.fx * (1.f - g.fy);
+        const float w10 = (1.f - g.fx) * g.fy, w11 = g.fx * g.fy;
+        for (int cell = lane; cell < FP; cell += 32) {
+            const int rr = cell / F, cc = cell - rr * F;
+            const int y = g.iy0 + rr, x = g.ix0 + cc;
+            if ((unsigned)y >= (unsigned)Hl || (unsigned)x >= (unsigned)Wl) continue;
+            // cell (rr,cc) receives tap (a=cc,b=rr)*w00 + (cc-1,rr)*w01 + (cc,rr-1)*w10 + (cc-1,rr-1)*w11
+            const bool a0 = cc < D, a1 = cc > 0, b0 = rr < D, b1 = rr > 0;
+            float acc = 0.f;
+            if (a0 && b0) acc = w00 * Gq[cc * D + rr];
+            if (a1 && b0) acc = fmaf(w01, Gq[(cc - 1) * D + rr], acc);
+            if (a0 && b1) acc = fmaf(w10, Gq[cc * D + rr - 1], acc);
+            if (a1 && b1) acc = fmaf(w11, Gq[(cc - 1) * D + rr - 1], acc);
+            red_add(dst + y * Wl + x, acc);
+        }
     }
 }
 
