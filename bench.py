@@ -33,8 +33,8 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "pcfa_closure_evals_per_sec"
-UNIT = "closures/s"
+METRIC = "PCFA steps/sec (fwd+bwd, device-timed)"      # BASELINE.json metric; 1 step = 1 closure evaluation
+UNIT = "steps/s"
 H_IMG, W_IMG = 436, 1024
 DELTA_BOUND, EPS_BOX = 0.005, 1e-7
 MU = 2500.0 / DELTA_BOUND           # attack_PCFA.py:578-583, zero target
@@ -122,6 +122,17 @@ def prepare_on_device(i1, i2, device):
 
 def init_vars(img):
     return torch.atanh(2.0 * (1.0 - EPS_BOX) * img - (1 - EPS_BOX)).contiguous()
+
+
+def measured_traffic(entry_point):
+    """dram bytes per launch from this round's ncu --set full capture (profiles/traffic_r*.json), or None."""
+    files = sorted((ROOT / "profiles").glob("traffic_r*.json"))
+    if not files:
+        return None
+    try:
+        return json.loads(files[-1].read_text())["entry_points"].get(entry_point)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -250,7 +261,7 @@ def run_b200(args):
            "data": "synthetic", "config": config_dict(args, world),
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-           "cuda_graph": graph is not None, "clocks": clocks.summary(), "loss": float(fo.terms[0].item())}
+           "cuda_graph": graph is not None, "cudnn_benchmark": not args.no_cudnn_benchmark, "clocks": clocks.summary(), "loss": float(fo.terms[0].item())}
 
     if rank == 0:
         # ---- per-kernel roofline, instrumented eager pass on the launching stream
@@ -261,7 +272,10 @@ def run_b200(args):
         top = max(table, key=lambda r: r["total_us_per_step"]) if table else None
         if top:
             out["roofline"] = {"bound": "hbm", "kernel": top["name"], "achieved": top["achieved_gbs"], "peak": peak,
-                               "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4), "traffic": None,
+                               "unit": "GB/s", "frac": round(top["achieved_gbs"] / peak, 4),
+                               "traffic": measured_traffic(top["name"]),
+                               "algorithmic_bytes": top["algorithmic_bytes"], "avg_us": top["avg_us"],
+                               "launches_per_step": top["launches_per_step"],
                                "peak_source": peak_src,
                                "how": "CUDA events around each launch in an eager pass of the same step (graph replay cannot be event-bracketed per kernel)"}
         if world == 1 and not args.no_cpu_baseline:
