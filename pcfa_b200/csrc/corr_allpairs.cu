@@ -11,7 +11,7 @@ namespace pcfa {
 // --- tcgen05 variant (corr_allpairs_tc.cu) -------------------------------------------------
 int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyramid, void* ws,
                             int64_t ws_bytes, int B, int C, int H, int W, int levels,
-                            cudaStream_t s);
+                            cudaStream_t s, int two_cta);
 int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels);
 // --- tcgen05 backward (corr_allpairs_bwd_tc.cu) ----------------------------------------------
@@ -185,12 +185,12 @@ extern "C" int pcfa_corr_pyramid_forward(const float* fmap1, const float* fmap2,
     if (!fmap1 || !fmap2 || !pyramid) return PCFA_E_BADARG;
     PCFA_TRY(pyramid_check(B, C, H, W, num_levels));
     const bool tc_ok = corr_pyramid_tc_supported(B, C, H, W, num_levels);
-    if (impl == 2 && !tc_ok) return PCFA_E_BADARG;
-    if (impl == 2 || (impl == 0 && tc_ok)) {
+    if ((impl == 2 || impl == 3) && !tc_ok) return PCFA_E_BADARG;
+    if (impl == 2 || impl == 3 || (impl == 0 && tc_ok)) {
         if (!workspace || workspace_bytes < corr_pyramid_tc_workspace_bytes(B, C, H, W, num_levels))
             return PCFA_E_WORKSPACE;
         return corr_pyramid_forward_tc(fmap1, fmap2, pyramid, workspace, workspace_bytes, B, C, H, W,
-                                       num_levels, as_stream(stream));
+                                       num_levels, as_stream(stream), impl == 2 ? 0 : 1);   // auto and 3: cta_group::2 pairs
     }
     return forward_simt(fmap1, fmap2, pyramid, B, C, H, W, num_levels, as_stream(stream));
 }
@@ -203,8 +203,8 @@ extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float
     if (!grad_pyramid || !fmap1 || !fmap2 || !grad_fmap1 || !grad_fmap2) return PCFA_E_BADARG;
     PCFA_TRY(pyramid_check(B, C, H, W, num_levels));
     const bool tc_ok = corr_pyramid_bwd_tc_supported(B, C, H, W, num_levels);
-    if (impl == 2 && !tc_ok) return PCFA_E_BADARG;
-    if (impl == 2 || (impl == 0 && tc_ok)) {
+    if ((impl == 2 || impl == 3) && !tc_ok) return PCFA_E_BADARG;
+    if (impl == 2 || impl == 3 || (impl == 0 && tc_ok)) {
         if (!workspace || workspace_bytes < corr_pyramid_bwd_tc_workspace_bytes(B, C, H, W, num_levels))
             return PCFA_E_WORKSPACE;
         return corr_pyramid_backward_tc(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace,

@@ -45,6 +45,9 @@ struct TcParams {
     long long lvl_off[TC_MAX_LEVELS];
     long long total_tiles;
     float scale;
+    // 2-CTA variant: work item = (sample, pair of query blocks, pair of target tiles)
+    int qb2blocks, pairs_per_qb2;
+    long long total_pairs;
 };
 
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128.
@@ -208,6 +211,224 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// ------------------------------------------------------------------------------------ 2-CTA kernel
+// Same algorithm on CTA pairs (cta_group::2): one tcgen05.mma covers M = 256 targets (two 8x16 patches, one per
+// CTA) x N = 256 queries (two query blocks, one resident in each CTA's shared memory).  Per MMA cycle each CTA
+// now streams HALF the target bytes of the single-CTA kernel, which was limited by the L2->SM operand stream
+// (tensor pipe 49 % active).  Both CTAs run a TMA producer (loads signal the LEADER's mbarriers through the
+// .cta_group::2 form); only the leader issues MMAs; tcgen05.commit multicasts "slot free"/"accumulator full"
+// to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's barrier (remote arrive).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leader_bar(uint32_t bar) { return bar & 0xFEFFFFFFu; }   // peer bit -> even CTA
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint32_t bar) {     // arrive on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {  // arrive on the leader's copy of `bar`
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t"
+        "}" ::"r"(bar), "r"(0) : "memory");
+}
+constexpr uint32_t kIdescBf16_2cta = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct PairCoord { int b, qb2, level, ty, tx; bool valid; long long key; };
+__device__ __forceinline__ PairCoord decode_pair(long long t, int rank, const TcParams& P) {
+    PairCoord c;
+    c.key = t / P.pairs_per_qb2;
+    const int pt = (int)(t - c.key * P.pairs_per_qb2);
+    c.b = (int)(c.key / P.qb2blocks);
+    c.qb2 = (int)(c.key - (long long)c.b * P.qb2blocks);
+    int nt = 2 * pt + rank;
+    c.valid = nt < P.tiles_per_qb;
+    if (!c.valid) nt = 0;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < TC_MAX_LEVELS; ++i)
+        if (i < P.levels && nt >= P.tile_off[i]) l = i;
+    nt -= P.tile_off[l];
+    c.level = l;
+    c.ty = nt / P.tiles_x[l];
+    c.tx = nt - c.ty * P.tiles_x[l];
+    return c;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, float* __restrict__ pyr) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_q = base;
+    const uint32_t smem_a = base + 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES;
+    const uint32_t bars = smem_a + TC_STAGES * 2 * TC_TILE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES;
+    const uint32_t bar_qfull = bars + 16 * TC_STAGES, bar_qempty = bar_qfull + 8;
+    const uint32_t bar_tfull = bar_qempty + 8, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const long long ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const long long t_begin = P.total_pairs * cid / ncl, t_end = P.total_pairs * (cid + 1) / ncl;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        int stage = 0; uint32_t phase = 0, qphase = 0;
+        long long cur = -1;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const PairCoord c = decode_pair(t, rank, P);
+            if (c.key != cur) {
+                mbar_wait(bar_qempty, qphase ^ 1);
+                if (rank == 0) mbar_expect_tx(bar_qfull, 2 * 2 * P.kchunks * TC_TILE_BYTES);     // both CTAs' bytes
+                for (int part = 0; part < 2; ++part)
+                    for (int kc = 0; kc < P.kchunks; ++kc)
+                        tma2_load_3d(smem_q + (part * TC_MAX_KCHUNKS + kc) * TC_TILE_BYTES, &maps.q, leader_bar(bar_qfull),
+                                     kc * TC_BK, (2 * c.qb2 + rank) * TC_BN, part * P.B + c.b);
+                qphase ^= 1;
+                cur = c.key;
+            }
+            // an absent second tile of an odd tile count reads a fully out-of-range box: zero-filled
+            const int y0 = c.valid ? c.ty * TC_PH : (P.lh[0] + TC_PH), x0 = c.tx * TC_PW;
+            for (int kc = 0; kc < P.kchunks; ++kc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * 2 * TC_TILE_BYTES);
+                const uint32_t dst = smem_a + stage * 2 * TC_TILE_BYTES;
+                const uint32_t lb = leader_bar(bar_full + 8 * stage);
+                tma2_load_4d(dst, &maps.t[c.level], lb, kc * TC_BK, x0, y0, c.b);
+                tma2_load_4d(dst + TC_TILE_BYTES, &maps.t[c.level], lb, kc * TC_BK, x0, y0, P.B + c.b);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        int stage = 0; uint32_t phase = 0, qphase = 0, acc = 0, accphase = 0;
+        long long cur = -1;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const long long key = t / P.pairs_per_qb2;
+            if (key != cur) { mbar_wait(bar_qfull, qphase); qphase ^= 1; cur = key; }
+            mbar_wait(bar_tempty + 8 * acc, accphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kc = 0; kc < P.kchunks; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_a + stage * 2 * TC_TILE_BYTES, a_mid = a_hi + TC_TILE_BYTES;
+                const uint32_t b_hi = smem_q + kc * TC_TILE_BYTES, b_mid = smem_q + (TC_MAX_KCHUNKS + kc) * TC_TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                    const uint32_t ko = kk * 32;
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, (kc | kk) != 0);
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16_2cta, 1);
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_mid + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, 1);
+                }
+                tc2_commit_mc(bar_empty + 8 * stage);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc2_commit_mc(bar_tfull + 8 * acc);
+            const bool last_of_block = (t + 1 == t_end) || ((t + 1) / P.pairs_per_qb2 != key);
+            if (last_of_block) tc2_commit_mc(bar_qempty);
+            acc ^= 1;
+            if (acc == 0) accphase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (8 warps, both CTAs)
+        const int ew = warp & 3, half = (warp - 4) >> 2;       // TMEM lanes [32*ew,+32), query columns [128*half,+128)
+        const int p = ew * 32 + lane;
+        const int yl = p / TC_PW, xl = p % TC_PW;
+        uint32_t acc = 0, accphase = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const PairCoord c = decode_pair(t, rank, P);
+            const int Hl = P.lh[c.level], Wl = P.lw[c.level];
+            const int y = c.ty * TC_PH + yl, x = c.tx * TC_PW + xl;
+            const bool ok = c.valid && (y < Hl) && (x < Wl);
+            const long long qstride = (long long)Hl * Wl;
+            const int q0 = c.qb2 * 256 + half * 128;
+            float* out = pyr + P.lvl_off[c.level] + ((long long)c.b * P.N + q0) * qstride + (long long)y * Wl + x;
+            const int nq = P.N - q0;                                // valid queries from q0 on (may be <= 0)
+            mbar_wait(bar_tfull + 8 * acc, accphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256 + half * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+                uint32_t v0[32], v1[32];
+                tc_ld32(taddr + c0, v0);
+                tc_ld32(taddr + c0 + 32, v1);
+                tc_wait_ld();
+                if (c0 == 64) {                                     // accumulator fully in registers: release it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta0(bar_tempty + 8 * acc);
+                }
+                if (ok) {
+                    if (nq >= c0 + 64) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v0[j])); out += qstride; }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (c0 + j < nq) __stcs(out, __uint_as_float(v0[j])); out += qstride; }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { if (c0 + 32 + j < nq) __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                    }
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) accphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -377,7 +598,7 @@ static int split_transpose(const float* src, __nv_bfloat16* dst, int B, int C, i
 }
 
 int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyramid, void* ws, int64_t ws_bytes,
-                            int B, int C, int H, int W, int levels, cudaStream_t s) {
+                            int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) return PCFA_E_NODEVICE;
     const TcWorkspace wl = tc_workspace(B, C, H, W, levels);
@@ -436,6 +657,20 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     P.total_tiles = (long long)B * P.qblocks * toff;
 
     const int smem = 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES + TC_STAGES * 2 * TC_TILE_BYTES + 1024 + 256;
+    if (two_cta) {
+        P.qb2blocks = ceil_div(P.qblocks, 2);
+        P.pairs_per_qb2 = ceil_div(toff, 2);
+        P.total_pairs = (long long)B * P.qb2blocks * P.pairs_per_qb2;
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr2_set = true;
+        }
+        long long clusters = tc_num_sms() / 2;
+        if (clusters > P.total_pairs) clusters = P.total_pairs;
+        corr_pyramid_tc2_kernel<<<(int)(2 * clusters), TC_THREADS, smem, s>>>(maps, P, pyramid);
+        return after_launch();
+    }
     static bool attr_set = false;
     if (!attr_set) {
         PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

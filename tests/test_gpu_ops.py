@@ -291,12 +291,14 @@ def _build_pyramid(f1, f2, levels, impl):
 
 @pytest.mark.parametrize("shape,levels", [((1, 64, 16, 24), 4), ((2, 128, 18, 27), 4), ((1, 256, 9, 17), 3),
                                           ((3, 64, 8, 8), 2), ((1, 256, 55, 128), 4), ((2, 256, 46, 62), 4)])
-def test_allpairs_tcgen05_matches_fp32_simt(shape, levels):
-    """bf16x3 tensor-core pyramid vs the exact-fp32 SIMT pyramid (which the oracle tests pin)."""
+@pytest.mark.parametrize("impl", [2, 3])
+def test_allpairs_tcgen05_matches_fp32_simt(shape, levels, impl):
+    """bf16x3 tensor-core pyramid (impl 2: one CTA per tile, impl 3: cta_group::2 pairs) vs the exact-fp32
+    SIMT pyramid (which the oracle tests pin)."""
     g = torch.Generator().manual_seed(sum(shape))
     f1 = torch.randn(shape, generator=g).cuda() * 3
     f2 = torch.randn(shape, generator=g).cuda() * 3
-    tc, offs = _build_pyramid(f1, f2, levels, 2)
+    tc, offs = _build_pyramid(f1, f2, levels, impl)
     simt, _ = _build_pyramid(f1, f2, levels, 1)
     assert torch.isfinite(tc).all(), "tensor-core path left pyramid cells unwritten"
     for l in range(levels):
