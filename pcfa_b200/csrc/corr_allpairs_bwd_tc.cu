@@ -240,10 +240,10 @@ __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
 }
 __global__ void __launch_bounds__(256)
 bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPrepArgs a) {
-    __shared__ float t0[32][8][33];
-    __shared__ float t1[32][4][17];
-    __shared__ float t2[32][2][9];
-    __shared__ float t3[32][1][5];
+    __shared__ float t0[32][8 * 33 + 1];     // odd per-channel strides: conflict-free fills and drains
+    __shared__ float t1[32][4 * 17 + 1];
+    __shared__ float t2[32][2 * 9 + 1];
+    __shared__ float t3[32][5];
     const int H = a.h[0], W = a.w[0];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const int cblocks = ceil_div(a.C, 32);
@@ -268,21 +268,21 @@ bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPre
         return;
     }
     for (int c = 0; c < 32; ++c)
-        t0[c][ty][tx] = (inb && c0 + c < a.C) ? __ldg(f2 + ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x) * a.alpha : 0.f;
+        t0[c][ty * 33 + tx] = (inb && c0 + c < a.C) ? __ldg(f2 + ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x) * a.alpha : 0.f;
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
         const int c = e / 64, r = (e / 16) % 4, q = e % 16;
-        t1[c][r][q] = 0.25f * ((t0[c][2 * r][2 * q] + t0[c][2 * r][2 * q + 1]) + (t0[c][2 * r + 1][2 * q] + t0[c][2 * r + 1][2 * q + 1]));
+        t1[c][r * 17 + q] = 0.25f * ((t0[c][(2 * r) * 33 + 2 * q] + t0[c][(2 * r) * 33 + 2 * q + 1]) + (t0[c][(2 * r + 1) * 33 + 2 * q] + t0[c][(2 * r + 1) * 33 + 2 * q + 1]));
     }
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * 2 * 8; e += 256) {
         const int c = e / 16, r = (e / 8) % 2, q = e % 8;
-        t2[c][r][q] = 0.25f * ((t1[c][2 * r][2 * q] + t1[c][2 * r][2 * q + 1]) + (t1[c][2 * r + 1][2 * q] + t1[c][2 * r + 1][2 * q + 1]));
+        t2[c][r * 9 + q] = 0.25f * ((t1[c][(2 * r) * 17 + 2 * q] + t1[c][(2 * r) * 17 + 2 * q + 1]) + (t1[c][(2 * r + 1) * 17 + 2 * q] + t1[c][(2 * r + 1) * 17 + 2 * q + 1]));
     }
     __syncthreads();
     if (threadIdx.x < 32 * 4) {
         const int c = threadIdx.x / 4, q = threadIdx.x % 4;
-        t3[c][0][q] = 0.25f * ((t2[c][0][2 * q] + t2[c][0][2 * q + 1]) + (t2[c][1][2 * q] + t2[c][1][2 * q + 1]));
+        t3[c][q] = 0.25f * ((t2[c][2 * q] + t2[c][2 * q + 1]) + (t2[c][9 + 2 * q] + t2[c][9 + 2 * q + 1]));
     }
     __syncthreads();
     for (int l = 0; l < a.levels; ++l) {
@@ -293,7 +293,7 @@ bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPre
             const int r = cell / ww, q = cell - r * ww;
             const int yy = (y0 >> l) + r, xx = (x0 >> l) + q;
             if (yy >= Hl || xx >= Wl || c0 + c >= a.C) continue;
-            const float v = (l == 0) ? t0[c][r][q] : (l == 1) ? t1[c][r][q] : (l == 2) ? t2[c][r][q] : t3[c][r][q];
+            const float v = (l == 0) ? t0[c][r * 33 + q] : (l == 1) ? t1[c][r * 17 + q] : (l == 2) ? t2[c][r * 9 + q] : t3[c][q];
             const long long o = (((long long)b * a.C + c0 + c) * Hl + yy) * Wl + xx;
             float hi, lo;
             tf32_split(v, &hi, &lo);
@@ -317,23 +317,24 @@ __global__ void bw_avgpool2_kernel(const float* __restrict__ in, float* __restri
     }
 }
 
-// grad_fmap2[r, y, x] += sum_{l>=1} gP_l[r, y>>l, x>>l] * 0.25^l
+// grad_fmap2[r, y, x] += sum_{l>=1} gP_l[r, y>>l, x>>l] * 0.25^l   (adjoint of the successive floor pooling).
+// grid: (ceil(W/128), H, R) with 128 threads: no index divisions, coalesced rows.
 struct BwUnpool { const float* g[BW_MAX_LEVELS]; int h[BW_MAX_LEVELS], w[BW_MAX_LEVELS]; int levels; };
-__global__ void bw_unpool_kernel(float* __restrict__ gf2, BwUnpool a, long long R, int H, int W) {
-    const long long total = R * H * W;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % W);
-        const int y = (int)((idx / W) % H);
-        const long long r = idx / ((long long)W * H);
-        float acc = gf2[idx], sc = 1.f;
-        for (int l = 1; l < a.levels; ++l) {
-            sc *= 0.25f;
-            const int yy = y >> l, xx = x >> l;
-            if (yy < a.h[l] && xx < a.w[l]) acc += sc * a.g[l][(r * a.h[l] + yy) * (long long)a.w[l] + xx];
-        }
-        gf2[idx] = acc;
+__global__ void __launch_bounds__(128)
+bw_unpool_kernel(float* __restrict__ gf2, const BwUnpool a, int H, int W) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    const long long r = blockIdx.z;
+    if (x >= W) return;
+    const long long idx = (r * H + y) * W + x;
+    float acc = gf2[idx], sc = 1.f;
+#pragma unroll
+    for (int l = 1; l < BW_MAX_LEVELS; ++l) {
+        if (l >= a.levels) break;
+        sc *= 0.25f;
+        const int yy = y >> l, xx = x >> l;
+        if (yy < a.h[l] && xx < a.w[l]) acc = fmaf(sc, __ldg(a.g[l] + (r * a.h[l] + yy) * a.w[l] + xx), acc);
     }
+    gf2[idx] = acc;
 }
 
 struct BwWorkspace { int64_t f1_split, p_split[BW_MAX_LEVELS], pooled[BW_MAX_LEVELS], gp[BW_MAX_LEVELS], total; };
@@ -476,8 +477,9 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
             u.g[l] = (l == 0) ? gf2 : reinterpret_cast<const float*>(wsb + wl.gp[l]);
             u.h[l] = L.h[l]; u.w[l] = L.w[l];
         }
-        const long long total = (long long)B * C * N;
-        bw_unpool_kernel<<<grid1(total), 256, 0, s>>>(gf2, u, (long long)B * C, H, W);
+        dim3 ugrid(ceil_div(W, 128), H, B * C);
+        if (ugrid.z > 65535 || H > 65535) return PCFA_E_TOOLARGE;
+        bw_unpool_kernel<<<ugrid, 128, 0, s>>>(gf2, u, H, W);
         PCFA_TRY(after_launch());
     }
     return PCFA_OK;

@@ -460,61 +460,78 @@ split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict_
 
 // Fused operand prep for the target side: one pass over fmap2 produces the channel-last bf16 hi/mid planes of
 // pool_l(fmap2) for every level (successive 2x2 floor pooling, as F.avg_pool2d applied level by level).
-// CTA = 32 channels x (8 rows x 32 cols) of level 0: coalesced 128-byte row reads, 64-byte channel runs out.
+// CTA = 32 channels x (8 rows x 32 cols) of level 0: coalesced 128-byte row reads; each thread then owns a
+// channel PAIR of one cell and writes bf16x2, so a warp stores two 64-byte channel runs (full sectors).
+// Shared tiles use an odd per-channel stride (conflict-free for both the row-wise fill and the channel-wise drain).
 struct TcPrepArgs {
     __nv_bfloat16* dst[TC_MAX_LEVELS];     // hi plane base per level; mid plane at + plane[l]
     long long plane[TC_MAX_LEVELS];        // B * H_l * W_l * C
     int h[TC_MAX_LEVELS], w[TC_MAX_LEVELS];
     int levels, B, C;
 };
+constexpr int PT_S0 = 8 * 33 + 1, PT_S1 = 4 * 17 + 1, PT_S2 = 2 * 9 + 1, PT_S3 = 5;
+
+template <int LVL>
+__device__ __forceinline__ void prep_targets_drain(const float* __restrict__ t, int cstride, int rstride,
+                                                   __nv_bfloat16* __restrict__ dst, long long plane, int Hl, int Wl,
+                                                   int C, int b, int c0, int y0, int x0) {
+    constexpr int hh = 8 >> LVL, ww = 32 >> LVL, cells = hh * ww;
+    for (int item = threadIdx.x; item < cells * 16; item += 256) {
+        const int cp = item & 15, cell = item >> 4;
+        const int r = cell / ww, q = cell % ww;
+        const int y = (y0 >> LVL) + r, x = (x0 >> LVL) + q;
+        if (y >= Hl || x >= Wl) continue;
+        const float v0 = t[(2 * cp) * cstride + r * rstride + q], v1 = t[(2 * cp + 1) * cstride + r * rstride + q];
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+        const __nv_bfloat162 mid = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+        const long long o = (((long long)b * Hl + y) * Wl + x) * C + c0 + 2 * cp;
+        *reinterpret_cast<__nv_bfloat162*>(dst + o) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(dst + plane + o) = mid;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-prep_targets_kernel(const float* __restrict__ src, TcPrepArgs a) {
-    __shared__ float t0[32][8][33];     // [c][y][x] level 0 (padded)
-    __shared__ float t1[32][4][17];
-    __shared__ float t2[32][2][9];
-    __shared__ float t3[32][1][5];
+prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
+    __shared__ float t0[32 * PT_S0];
+    __shared__ float t1[32 * PT_S1];
+    __shared__ float t2[32 * PT_S2];
+    __shared__ float t3[32 * PT_S3];
     const int H = a.h[0], W = a.w[0];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const int cblocks = a.C / 32;
     const int b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
-    for (int c = 0; c < 32; ++c) {
+    {
         const int y = y0 + ty, x = x0 + tx;
-        t0[c][ty][tx] = (y < H && x < W) ? __ldg(src + (((long long)b * a.C + c0 + c) * H + y) * W + x) : 0.f;
+        const bool inb = y < H && x < W;
+        const float* p = src + (((long long)b * a.C + c0) * H + y) * W + x;
+        const long long cs = (long long)H * W;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) t0[c * PT_S0 + ty * 33 + tx] = inb ? __ldg(p + c * cs) : 0.f;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
-        const int c = e / 64, r = (e / 16) % 4, q = e % 16;
-        t1[c][r][q] = 0.25f * ((t0[c][2 * r][2 * q] + t0[c][2 * r][2 * q + 1]) + (t0[c][2 * r + 1][2 * q] + t0[c][2 * r + 1][2 * q + 1]));
+    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
+        const int c = e >> 6, r = (e >> 4) & 3, q = e & 15;
+        const float* s0 = t0 + c * PT_S0 + (2 * r) * 33 + 2 * q;
+        t1[c * PT_S1 + r * 17 + q] = 0.25f * ((s0[0] + s0[1]) + (s0[33] + s0[34]));
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 2 * 8; e += 256) {
-        const int c = e / 16, r = (e / 8) % 2, q = e % 8;
-        t2[c][r][q] = 0.25f * ((t1[c][2 * r][2 * q] + t1[c][2 * r][2 * q + 1]) + (t1[c][2 * r + 1][2 * q] + t1[c][2 * r + 1][2 * q + 1]));
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+        const int c = e >> 4, r = (e >> 3) & 1, q = e & 7;
+        const float* s1 = t1 + c * PT_S1 + (2 * r) * 17 + 2 * q;
+        t2[c * PT_S2 + r * 9 + q] = 0.25f * ((s1[0] + s1[1]) + (s1[17] + s1[18]));
     }
     __syncthreads();
     if (threadIdx.x < 32 * 4) {
-        const int c = threadIdx.x / 4, q = threadIdx.x % 4;
-        t3[c][0][q] = 0.25f * ((t2[c][0][2 * q] + t2[c][0][2 * q + 1]) + (t2[c][1][2 * q] + t2[c][1][2 * q + 1]));
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const float* s2 = t2 + c * PT_S2 + 2 * q;
+        t3[c * PT_S3 + q] = 0.25f * ((s2[0] + s2[1]) + (s2[9] + s2[10]));
     }
     __syncthreads();
-    // write: lane = channel (contiguous in the channel-last layout), loop over the cells of each level
-    const int c = threadIdx.x & 31, slot = threadIdx.x >> 5;
-    for (int l = 0; l < a.levels; ++l) {
-        const int hh = 8 >> l, ww = 32 >> l;
-        const int Hl = a.h[l], Wl = a.w[l];
-        for (int cell = slot; cell < hh * ww; cell += 8) {
-            const int r = cell / ww, q = cell % ww;
-            const int y = (y0 >> l) + r, x = (x0 >> l) + q;
-            if (y >= Hl || x >= Wl) continue;
-            const float v = (l == 0) ? t0[c][r][q] : (l == 1) ? t1[c][r][q] : (l == 2) ? t2[c][r][q] : t3[c][r][q];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
-            const long long o = (((long long)b * Hl + y) * Wl + x) * a.C + c0 + c;
-            a.dst[l][o] = hi;
-            a.dst[l][a.plane[l] + o] = mid;
-        }
-    }
+    prep_targets_drain<0>(t0, PT_S0, 33, a.dst[0], a.plane[0], a.h[0], a.w[0], a.C, b, c0, y0, x0);
+    if (a.levels > 1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0);
+    if (a.levels > 2) prep_targets_drain<2>(t2, PT_S2, 9, a.dst[2], a.plane[2], a.h[2], a.w[2], a.C, b, c0, y0, x0);
+    if (a.levels > 3) prep_targets_drain<3>(t3, PT_S3, 5, a.dst[3], a.plane[3], a.h[3], a.w[3], a.C, b, c0, y0, x0);
 }
 
 __global__ void tc_avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int Hi,
