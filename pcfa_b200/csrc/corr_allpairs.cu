@@ -16,7 +16,7 @@ int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels);
 // --- tcgen05 backward (corr_allpairs_bwd_tc.cu) ----------------------------------------------
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
-                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s);
+                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta);
 int64_t corr_pyramid_bwd_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_bwd_tc_supported(int B, int C, int H, int W, int levels);
 
@@ -208,7 +208,7 @@ extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float
         if (!workspace || workspace_bytes < corr_pyramid_bwd_tc_workspace_bytes(B, C, H, W, num_levels))
             return PCFA_E_WORKSPACE;
         return corr_pyramid_backward_tc(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace,
-                                        workspace_bytes, B, C, H, W, num_levels, as_stream(stream));
+                                        workspace_bytes, B, C, H, W, num_levels, as_stream(stream), impl == 2 ? 0 : 1);
     }
     const int64_t need = 2 * pooled_floats(B, C, H, W, num_levels) * (int64_t)sizeof(float);
     if (need > 0 && (!workspace || workspace_bytes < need)) return PCFA_E_WORKSPACE;

@@ -208,6 +208,172 @@ corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P
     }
 }
 
+// ------------------------------------------------------------------------------------ CTA-pair variant
+// cta_group::2: one MMA covers M = 256 rows (one 128-row block per CTA) x N = C channels, whose operand is split
+// across the pair (each CTA streams C/2 channel rows).  With two accumulators per CTA a pair owns FOUR row blocks
+// per streamed channel chunk: per MMA cycle each CTA streams 64 KB / 2048 cyc instead of 96 KB / 2048 cyc, and
+// the smaller stage makes room for a 3-deep ring.  Barrier protocol as in corr_pyramid_tc2_kernel.
+constexpr int BW2_STAGES = 3;
+
+__device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, const BwParams& P, int rank) {
+    BwSegment sg;
+    const long long ug = w / P.chunks_total;
+    sg.k0 = (int)(w - ug * P.chunks_total);
+    const long long unit_end = (ug + 1) * P.chunks_total;
+    sg.next = unit_end < w_end ? unit_end : w_end;
+    sg.k1 = sg.k0 + (int)(sg.next - w);
+    sg.b = (int)(ug / P.units_per_sample);
+    const int unit = (int)(ug - (long long)sg.b * P.units_per_sample);
+    int level = 0, quad = unit;
+    if (P.pass == 2) {
+#pragma unroll
+        for (int l = 1; l < BW_MAX_LEVELS; ++l)
+            if (l < P.levels && unit >= P.unit_off[l]) level = l;
+        quad = unit - P.unit_off[level];
+    }
+    sg.level = level;
+    sg.rows_total = (P.pass == 1) ? P.N : P.nl[level];
+    sg.m0a = (quad * 4 + rank * 2) * BW_BM;          // this CTA's two row blocks (may lie past rows_total: zero-filled)
+    sg.m0b = sg.m0a + BW_BM;
+    sg.nblk = 2;
+    return sg;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BW_THREADS, 1)
+corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bh_bytes = (uint32_t)(P.C / 2) * 128u;               // this CTA's half of a [C x 32 tf32] tile
+    const uint32_t stage_bytes = 2 * BW_A_BYTES + 2 * bh_bytes;
+    const uint32_t bars = base + BW2_STAGES * stage_bytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW2_STAGES;
+    const uint32_t bar_accfull = bar_empty + 8 * BW2_STAGES, bar_accempty = bar_accfull + 8;
+    const uint32_t tmem_slot = bar_accempty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const long long ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const long long w_begin = P.work_total * cid / ncl, w_end = P.work_total * (cid + 1) / ncl;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BW2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_accfull, 1);
+        mbar_init(bar_accempty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        int stage = 0; uint32_t phase = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw2_segment(w, w_end, P, rank);
+            for (int kc = sg.k0; kc < sg.k1; ++kc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t dst = base + stage * stage_bytes;
+                const uint32_t full = leader_bar(bar_full + 8 * stage);
+                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * stage_bytes);       // both CTAs' bytes
+                const int crow = rank * (P.C / 2);
+                if (P.pass == 1) {
+                    int l = 0;
+#pragma unroll
+                    for (int i = 1; i < BW_MAX_LEVELS; ++i)
+                        if (i < P.levels && kc >= P.chunk_off[i]) l = i;
+                    const int j0 = (kc - P.chunk_off[l]) * BW_BK;
+                    tma2_load_3d(dst, &maps.a[l], full, j0, sg.m0a, sg.b);
+                    tma2_load_3d(dst + BW_A_BYTES, &maps.a[l], full, j0, sg.m0b, sg.b);
+                    tma2_load_3d(dst + 2 * BW_A_BYTES, &maps.b[l], full, j0, crow, sg.b);
+                    tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[l], full, j0, crow, P.B + sg.b);
+                } else {
+                    const int i0 = kc * BW_BK;
+                    for (int g = 0; g < 4; ++g) {
+                        tma2_load_3d(dst + g * 4096, &maps.a[sg.level], full, sg.m0a + 32 * g, i0, sg.b);
+                        tma2_load_3d(dst + BW_A_BYTES + g * 4096, &maps.a[sg.level], full, sg.m0b + 32 * g, i0, sg.b);
+                    }
+                    tma2_load_3d(dst + 2 * BW_A_BYTES, &maps.b[0], full, i0, crow, sg.b);
+                    tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[0], full, i0, crow, P.B + sg.b);
+                }
+                if (++stage == BW2_STAGES) { stage = 0; phase ^= 1; }
+            }
+            w = sg.next;
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===================================================================== MMA issuer (leader only)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((P.pass == 2 ? 1u : 0u) << 15) |
+                               ((uint32_t)(P.C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        int stage = 0; uint32_t phase = 0, accphase = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw2_segment(w, w_end, P, 0);
+            mbar_wait(bar_accempty, accphase ^ 1);
+            tc_fence_after();
+            for (int kc = sg.k0; kc < sg.k1; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = base + stage * stage_bytes, sb_hi = sa + 2 * BW_A_BYTES, sb_lo = sb_hi + bh_bytes;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint32_t d_tmem = tmem_base + r * P.C;
+#pragma unroll
+                    for (int kk = 0; kk < BW_BK / 8; ++kk) {
+                        const uint64_t ad = (P.pass == 1) ? umma_desc_sw128(sa + r * BW_A_BYTES + kk * 32)
+                                                          : umma_desc_mn_tf32(sa + r * BW_A_BYTES + kk * 1024, 4096, 512);
+                        tc2_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_hi + kk * 32), idesc, (kc != sg.k0) || (kk != 0));
+                        tc2_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_lo + kk * 32), idesc, 1);
+                    }
+                }
+                tc2_commit_mc(bar_empty + 8 * stage);
+                if (++stage == BW2_STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc2_commit_mc(bar_accfull);
+            accphase ^= 1;
+            w = sg.next;
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (per segment, both CTAs)
+        const int ew = warp & 3, r = (warp - 4) >> 2;
+        uint32_t accphase = 0;
+        for (long long w = w_begin; w < w_end;) {
+            const BwSegment sg = bw2_segment(w, w_end, P, rank);
+            mbar_wait(bar_accfull, accphase);
+            tc_fence_after();
+            const int m = (r == 0 ? sg.m0a : sg.m0b) + ew * 32 + lane;
+            float* out = P.out[(P.pass == 1) ? 0 : sg.level] + (long long)sg.b * P.C * sg.rows_total + m;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + r * P.C;
+            for (int c0 = 0; c0 < P.C; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr + c0, v);
+                tc_wait_ld();
+                if (m < sg.rows_total) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < P.C) red_add(out + (long long)(c0 + j) * sg.rows_total, __uint_as_float(v[j]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta0(bar_accempty);
+            accphase ^= 1;
+            w = sg.next;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+    }
+}
+
 // src fp32 [n] * scale  ->  hi = round-to-nearest TF32 (low 13 bits zero), lo = v - hi (exact in fp32)
 __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
                                   long long n, float scale) {
@@ -388,7 +554,8 @@ static int grid1(long long total) {
 }
 
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
-                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s) {
+                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
+    if (C % 32 != 0) two_cta = 0;                       // each CTA of a pair streams C/2 channel rows
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) return PCFA_E_NODEVICE;
     const BwWorkspace wl = bw_workspace(B, C, H, W, levels);
@@ -417,13 +584,30 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         PCFA_TRY(after_launch());
     }
 
-    const int smem = BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
-    static int smem_set = 0;
-    if (smem > smem_set) {
+    const int smem = two_cta ? BW2_STAGES * (2 * BW_A_BYTES + C * 128) + 1024 + 256
+                             : BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
+    static int smem_set = 0, smem2_set = 0;
+    if (!two_cta && smem > smem_set) {
         PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
     }
+    if (two_cta && smem > smem2_set) {
+        PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_pyramid_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem2_set = smem;
+    }
     const int sms = tc_num_sms();
+    const int group = two_cta ? 4 : 2;                  // row blocks per work unit
+    auto launch = [&](const BwMaps& maps, const BwParams& P) -> int {
+        if (two_cta) {
+            long long clusters = sms / 2;
+            if (clusters > P.work_total) clusters = P.work_total;
+            corr_pyramid_bwd_tc2_kernel<<<(int)(2 * clusters), BW_THREADS, smem, s>>>(maps, P);
+        } else {
+            const int grid = (int)(P.work_total < sms ? P.work_total : sms);
+            corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
+        }
+        return after_launch();
+    };
 
     // ---- pass I: grad_fmap1
     {
@@ -435,17 +619,15 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
             const int nl = L.h[l] * L.w[l];
             P.nl[l] = nl; P.chunk_off[l] = off; off += ceil_div(nl, BW_BK);
             PCFA_TRY(enc3(enc, &maps.a[l], gpyr + L.off[l], nl, N, B, BW_BK, BW_BM));
-            PCFA_TRY(enc3(enc, &maps.b[l], wsb + wl.p_split[l], nl, C, 2 * B, BW_BK, C));
+            PCFA_TRY(enc3(enc, &maps.b[l], wsb + wl.p_split[l], nl, C, 2 * B, BW_BK, two_cta ? C / 2 : C));
         }
         for (int l = levels; l <= BW_MAX_LEVELS; ++l) P.chunk_off[l] = off;
         for (int l = levels; l < BW_MAX_LEVELS; ++l) { maps.a[l] = maps.a[0]; maps.b[l] = maps.b[0]; }
         P.chunks_total = off;
-        P.units_per_sample = ceil_div(ceil_div(N, BW_BM), 2);
+        P.units_per_sample = ceil_div(ceil_div(N, BW_BM), group);
         P.work_total = (long long)B * P.units_per_sample * P.chunks_total;
         P.out[0] = gf1;
-        const int grid = (int)(P.work_total < sms ? P.work_total : sms);
-        corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
-        PCFA_TRY(after_launch());
+        PCFA_TRY(launch(maps, P));
     }
     // ---- pass II: grad of P_l (level 0 goes straight into grad_fmap2)
     {
@@ -455,20 +637,18 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         int off = 0;
         for (int l = 0; l < levels; ++l) {
             const int nl = L.h[l] * L.w[l];
-            P.nl[l] = nl; P.unit_off[l] = off; off += ceil_div(ceil_div(nl, BW_BM), 2);
+            P.nl[l] = nl; P.unit_off[l] = off; off += ceil_div(ceil_div(nl, BW_BM), group);
             PCFA_TRY(enc3(enc, &maps.a[l], gpyr + L.off[l], nl, N, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
             P.out[l] = (l == 0) ? gf2 : reinterpret_cast<float*>(wsb + wl.gp[l]);
         }
         for (int l = levels; l <= BW_MAX_LEVELS; ++l) P.unit_off[l] = off;
-        PCFA_TRY(enc3(enc, &maps.b[0], wsb + wl.f1_split, N, C, 2 * B, BW_BK, C));
+        PCFA_TRY(enc3(enc, &maps.b[0], wsb + wl.f1_split, N, C, 2 * B, BW_BK, two_cta ? C / 2 : C));
         for (int l = levels; l < BW_MAX_LEVELS; ++l) maps.a[l] = maps.a[0];
         for (int l = 1; l < BW_MAX_LEVELS; ++l) maps.b[l] = maps.b[0];
         P.chunks_total = ceil_div(N, BW_BK);
         P.units_per_sample = off;
         P.work_total = (long long)B * off * P.chunks_total;
-        const int grid = (int)(P.work_total < sms ? P.work_total : sms);
-        corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
-        PCFA_TRY(after_launch());
+        PCFA_TRY(launch(maps, P));
     }
     if (levels > 1) {
         BwUnpool u{};

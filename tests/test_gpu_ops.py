@@ -332,7 +332,8 @@ def _pyramid_backward(gp, f1, f2, levels, impl):
 
 @pytest.mark.parametrize("shape,levels", [((1, 64, 16, 32), 4), ((2, 128, 16, 24), 3), ((1, 256, 12, 20), 2),
                                           ((1, 256, 55, 128), 4), ((2, 256, 46, 64), 4), ((1, 48, 8, 8), 1)])
-def test_allpairs_backward_tcgen05_matches_fp32_simt(shape, levels):
+@pytest.mark.parametrize("impl", [2, 3])
+def test_allpairs_backward_tcgen05_matches_fp32_simt(shape, levels, impl):
     """TF32 tensor-core backward (K-major pass I, MN-major pass II) vs the exact-fp32 SIMT backward.
     Expected error: 2^-11 relative truncation of the gradient pyramid, random over the contraction."""
     from pcfa_b200.corr_block import pyramid_layout
@@ -342,7 +343,7 @@ def test_allpairs_backward_tcgen05_matches_fp32_simt(shape, levels):
     f2 = torch.randn(shape, generator=g).cuda()
     offs, _, _ = pyramid_layout(B, H, W, levels)
     gp = torch.randn(offs[-1], generator=g).cuda()
-    t1, t2 = _pyramid_backward(gp, f1, f2, levels, 2)
+    t1, t2 = _pyramid_backward(gp, f1, f2, levels, impl)      # 2: one CTA per block pair, 3: cta_group::2 pairs
     s1, s2 = _pyramid_backward(gp, f1, f2, levels, 1)
     for name, a, b in (("grad_fmap1", t1, s1), ("grad_fmap2", t2, s2)):
         assert torch.isfinite(a).all(), f"{name}: unwritten cells"
