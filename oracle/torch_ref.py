@@ -86,26 +86,28 @@ class _ScsFn(Function):
     def forward(ctx, a, b, k, patch, stride, pad, dil, dilp):
         ctx.save_for_backward(a, b)
         ctx.cfg = (k, patch, stride, pad, dil, dilp)
+        dev = a.device
+        a, b = a.detach().cpu().contiguous(), b.detach().cpu().contiguous()    # CPU-only sampler (PWCNet.py:18-21,48-49)
         be = _ref_scs_backend()
         if be is not None:
-            return be.forward(a.contiguous(), b.contiguous(), k, k, patch, patch, pad, pad, dil, dil, dilp, dilp,
-                              stride, stride)
-        return torch.from_numpy(cops.scs_forward(a.detach().numpy(), b.detach().numpy(), k, patch, stride, pad,
-                                                 dil, dilp))
+            out = be.forward(a, b, k, k, patch, patch, pad, pad, dil, dil, dilp, dilp, stride, stride)
+        else:
+            out = torch.from_numpy(cops.scs_forward(a.numpy(), b.numpy(), k, patch, stride, pad, dil, dilp))
+        return out.to(dev)
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         k, patch, stride, pad, dil, dilp = ctx.cfg
+        dev = a.device
+        a, b, g = a.detach().cpu().contiguous(), b.detach().cpu().contiguous(), g.detach().cpu().contiguous()
         be = _ref_scs_backend()
         if be is not None:
-            g1, g2 = be.backward(a.contiguous(), b.contiguous(), g.contiguous(), k, k, patch, patch, pad, pad, dil,
-                                 dil, dilp, dilp, stride, stride)
+            g1, g2 = be.backward(a, b, g, k, k, patch, patch, pad, pad, dil, dil, dilp, dilp, stride, stride)
         else:
-            g1, g2 = cops.scs_backward(a.detach().numpy(), b.detach().numpy(), g.numpy(), k, patch, stride, pad,
-                                       dil, dilp)
+            g1, g2 = cops.scs_backward(a.numpy(), b.numpy(), g.numpy(), k, patch, stride, pad, dil, dilp)
             g1, g2 = torch.from_numpy(g1), torch.from_numpy(g2)
-        return g1, g2, None, None, None, None, None, None
+        return g1.to(dev), g2.to(dev), None, None, None, None, None, None
 
 
 def spatial_correlation_sample(a, b, kernel_size=1, patch_size=1, stride=1, padding=0, dilation=1,
