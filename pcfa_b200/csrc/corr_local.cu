@@ -194,6 +194,252 @@ local_corr_bwd_k1s1(const float* __restrict__ other, const float* __restrict__ g
     }
 }
 
+// opaque 16-byte shared-memory load: keeps register-resident windows from being re-materialised as scalar LDS
+__device__ __forceinline__ float4 lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// ------------------------------------------------------------------ tiled fast paths (k = 1, stride 1)
+// Forward: CTA = (4-row x 32-col output tile, chunk of DYC displacement rows); channel chunks of CC are staged in
+// shared memory (in1 tile + the in2 halo tile), each thread owns 4 adjacent pixels x all D horizontal
+// displacements of one displacement row: one LDS.128 of in1 and NB4 LDS.128 of in2 feed 4*D FMAs per channel.
+template <int D, int DIL, int DYC, int TH, int CC>
+__global__ void __launch_bounds__(8 * DYC * TH)
+lc_fwd_tiled(const float* __restrict__ in1, const float* __restrict__ in2, float* __restrict__ out, LocalCorrGeom g) {
+    constexpr int TW = 32, RAD = (D - 1) / 2, R = RAD * DIL, BW = TW + 2 * R, BH = TH + (DYC - 1) * DIL;
+    constexpr int WIN = 4 + (D - 1) * DIL, NB4 = WIN / 4, NT = 8 * DYC * TH;
+    static_assert(WIN % 4 == 0 && R % 4 == 0 && BW % 4 == 0, "window must be float4-tileable");
+    extern __shared__ __align__(16) float lc_smem[];
+    float* As = lc_smem;                       // [CC][TH][TW]
+    float* Bs = lc_smem + CC * TH * TW;        // [CC][BH][BW]
+    const int tiles_x = ceil_div(g.oW, TW);
+    const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TH;
+    constexpr int NDYC = (D + DYC - 1) / DYC;
+    const int n = blockIdx.y / NDYC, dy0 = (blockIdx.y % NDYC) * DYC;
+    const int tid = threadIdx.x;
+    const int gx = tid & 7, tdy = (tid >> 3) % DYC, ty = tid / (8 * DYC);
+    const int64_t plane = (int64_t)g.iH * g.iW;
+    const float* a = in1 + (int64_t)n * g.C * plane;
+    const float* b = in2 + (int64_t)n * g.C * plane;
+    const int i2base = ty0 - g.padH + (dy0 - RAD) * DIL, j2base = tx0 - g.padW - R;
+    const bool vec = (g.iW % 4 == 0) && (g.padW % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16 == 0);
+
+    float acc[4][D];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[p][d] = 0.f;
+
+    for (int c0 = 0; c0 < g.C; c0 += CC) {
+        if (vec) {      // rows are 16-byte tileable: float4 loads, a chunk is entirely inside or outside the image
+            for (int e = tid; e < CC * TH * (TW / 4); e += NT) {
+                const int c = e / (TH * (TW / 4)), r = (e / (TW / 4)) % TH, x = (e % (TW / 4)) * 4;
+                const int i1 = ty0 + r - g.padH, j1 = tx0 + x - g.padW;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + c < g.C && (unsigned)i1 < (unsigned)g.iH && (unsigned)j1 < (unsigned)g.iW)
+                    v = __ldg(reinterpret_cast<const float4*>(a + (c0 + c) * plane + (int64_t)i1 * g.iW + j1));
+                *reinterpret_cast<float4*>(As + (c * TH + r) * TW + x) = v;
+            }
+            for (int e = tid; e < CC * BH * (BW / 4); e += NT) {
+                const int c = e / (BH * (BW / 4)), r = (e / (BW / 4)) % BH, x = (e % (BW / 4)) * 4;
+                const int i2 = i2base + r, j2 = j2base + x;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + c < g.C && (unsigned)i2 < (unsigned)g.iH && (unsigned)j2 < (unsigned)g.iW)
+                    v = __ldg(reinterpret_cast<const float4*>(b + (c0 + c) * plane + (int64_t)i2 * g.iW + j2));
+                *reinterpret_cast<float4*>(Bs + (c * BH + r) * BW + x) = v;
+            }
+        } else {
+        for (int e = tid; e < CC * TH * TW; e += NT) {
+            const int c = e / (TH * TW), r = (e / TW) % TH, x = e % TW;
+            const int i1 = ty0 + r - g.padH, j1 = tx0 + x - g.padW;
+            float v = 0.f;
+            if (c0 + c < g.C && (unsigned)i1 < (unsigned)g.iH && (unsigned)j1 < (unsigned)g.iW)
+                v = __ldg(a + (c0 + c) * plane + (int64_t)i1 * g.iW + j1);
+            As[e] = v;
+        }
+        for (int e = tid; e < CC * BH * BW; e += NT) {
+            const int c = e / (BH * BW), r = (e / BW) % BH, x = e % BW;
+            const int i2 = i2base + r, j2 = j2base + x;
+            float v = 0.f;
+            if (c0 + c < g.C && (unsigned)i2 < (unsigned)g.iH && (unsigned)j2 < (unsigned)g.iW)
+                v = __ldg(b + (c0 + c) * plane + (int64_t)i2 * g.iW + j2);
+            Bs[e] = v;
+        }
+        }
+        __syncthreads();
+        if (dy0 + tdy < D) {
+#pragma unroll 2
+            for (int c = 0; c < CC; ++c) {
+                const float4 a4 = *reinterpret_cast<const float4*>(As + (c * TH + ty) * TW + gx * 4);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float* brow = Bs + (c * BH + ty + tdy * DIL) * BW + gx * 4;
+                float bv[WIN];
+#pragma unroll
+                for (int k = 0; k < NB4; ++k) {
+                    const float4 t = lds128(brow + 4 * k);
+                    bv[4 * k] = t.x; bv[4 * k + 1] = t.y; bv[4 * k + 2] = t.z; bv[4 * k + 3] = t.w;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) acc[p][d] = fmaf(av[p], bv[p + d * DIL], acc[p][d]);
+            }
+        }
+        __syncthreads();
+    }
+    const int dyi = dy0 + tdy, h = ty0 + ty, w = tx0 + gx * 4;
+    if (dyi < D && h < g.oH && w < g.oW) {
+        float* o = out + ((((int64_t)n * D + dyi) * D) * g.oH + h) * g.oW + w;
+        const int64_t dstride = (int64_t)g.oH * g.oW;
+        const bool vst = (w + 3 < g.oW) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) && ((dstride & 3) == 0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (vst) {
+                *reinterpret_cast<float4*>(o + d * dstride) =
+                    make_float4(acc[0][d] * g.scale, acc[1][d] * g.scale, acc[2][d] * g.scale, acc[3][d] * g.scale);
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (w + p < g.oW) o[d * dstride + p] = acc[p][d] * g.scale;
+            }
+        }
+    }
+}
+
+// Backward: CTA = (one input row y, 32 columns, 32 channels); for each displacement row the matching row of
+// the other input (with halo) and the D gout rows (pre-shifted for WHICH == 2) are staged; each thread owns
+// 4 adjacent pixels of one channel, keeps the 4+(D-1)*DIL halo values in registers and does 4*D FMAs per
+// displacement row against one LDS.128 of gout per displacement.  Both gradients are gathers: no atomics.
+template <int D, int DIL, int WHICH, int CPT>
+__global__ void __launch_bounds__(256)
+lc_bwd_rows(const float* __restrict__ other, const float* __restrict__ gout, float* __restrict__ gin, LocalCorrGeom g) {
+    // CPT = channels per thread (2 amortises every gout LDS.128 over 8 FMAs; used when C >= 64)
+    constexpr int TW = 32, CHB = 32 * CPT, RAD = (D - 1) / 2, R = RAD * DIL, BW = TW + 2 * R;
+    constexpr int WIN = 4 + (D - 1) * DIL, NB4 = WIN / 4;
+    __shared__ __align__(16) float Os[CHB][BW];
+    __shared__ __align__(16) float Gs[D][TW];
+    const int tiles_x = ceil_div(g.iW, TW);
+    const int x0 = (blockIdx.x % tiles_x) * TW, y = blockIdx.x / tiles_x;
+    const int cblocks = ceil_div(g.C, CHB);
+    const int n = blockIdx.y / cblocks, c0 = (blockIdx.y % cblocks) * CHB;
+    const int tid = threadIdx.x, gx = tid & 7, cl = tid >> 3;
+    const int64_t plane = (int64_t)g.iH * g.iW, oplane = (int64_t)g.oH * g.oW;
+    const float* o = other + ((int64_t)n * g.C + c0) * plane;
+    const float* go = gout + (int64_t)n * D * D * oplane;
+    float acc[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+    const bool vec = (g.iW % 4 == 0) && (reinterpret_cast<uintptr_t>(o) % 16 == 0);
+
+    for (int dyi = 0; dyi < D; ++dyi) {
+        const int su = (dyi - RAD) * DIL;
+        const int yo = (WHICH == 1) ? y + su : y - su;              // row of the other input
+        const int h = ((WHICH == 1) ? y : y - su) + g.padH;          // gout row (out pixel of the in1 pixel)
+        __syncthreads();
+        if (vec) {
+            for (int e = tid; e < CHB * (BW / 4); e += 256) {
+                const int c = e / (BW / 4), q = (e % (BW / 4)) * 4;
+                const int xo = x0 - R + q;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + c < g.C && (unsigned)yo < (unsigned)g.iH && (unsigned)xo < (unsigned)g.iW)
+                    v = __ldg(reinterpret_cast<const float4*>(o + c * plane + (int64_t)yo * g.iW + xo));
+                *reinterpret_cast<float4*>(&Os[c][q]) = v;
+            }
+        } else {
+            for (int e = tid; e < CHB * BW; e += 256) {
+                const int c = e / BW, q = e % BW;
+                const int xo = x0 - R + q;
+                float v = 0.f;
+                if (c0 + c < g.C && (unsigned)yo < (unsigned)g.iH && (unsigned)xo < (unsigned)g.iW)
+                    v = __ldg(o + c * plane + (int64_t)yo * g.iW + xo);
+                Os[c][q] = v;
+            }
+        }
+        for (int e = tid; e < D * TW; e += 256) {
+            const int dxi = e / TW, xi = e % TW;
+            const int sv = (dxi - RAD) * DIL;
+            const int w = ((WHICH == 1) ? x0 + xi : x0 + xi - sv) + g.padW;
+            float v = 0.f;
+            if ((unsigned)h < (unsigned)g.oH && (unsigned)w < (unsigned)g.oW)
+                v = __ldg(go + ((int64_t)dyi * D + dxi) * oplane + (int64_t)h * g.oW + w);
+            Gs[dxi][xi] = v;
+        }
+        __syncthreads();
+        float bv[CPT][WIN];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const float* orow = &Os[cl + 32 * k][gx * 4];
+#pragma unroll
+            for (int q = 0; q < NB4; ++q) {
+                const float4 t = lds128(orow + 4 * q);
+                bv[k][4 * q] = t.x; bv[k][4 * q + 1] = t.y; bv[k][4 * q + 2] = t.z; bv[k][4 * q + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int dxi = 0; dxi < D; ++dxi) {
+            const float4 g4 = lds128(&Gs[dxi][gx * 4]);
+            const int sh = (WHICH == 1) ? dxi * DIL : (D - 1 - dxi) * DIL;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                acc[k][0] = fmaf(g4.x, bv[k][sh + 0], acc[k][0]);
+                acc[k][1] = fmaf(g4.y, bv[k][sh + 1], acc[k][1]);
+                acc[k][2] = fmaf(g4.z, bv[k][sh + 2], acc[k][2]);
+                acc[k][3] = fmaf(g4.w, bv[k][sh + 3], acc[k][3]);
+            }
+        }
+    }
+    const int x = x0 + gx * 4;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int c = c0 + cl + 32 * k;
+        if (c >= g.C || x >= g.iW) continue;
+        float* dst = gin + ((int64_t)n * g.C + c) * plane + (int64_t)y * g.iW + x;
+        if (x + 3 < g.iW && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[k][0] * g.scale, acc[k][1] * g.scale, acc[k][2] * g.scale, acc[k][3] * g.scale);
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (x + p < g.iW) dst[p] = acc[k][p] * g.scale;
+        }
+    }
+}
+
+template <int D, int DIL, int DYC, int TH, int CC>
+static int launch_lc_fwd(const float* in1, const float* in2, float* out, const LocalCorrGeom& g, cudaStream_t s) {
+    constexpr int R = (D - 1) / 2 * DIL, BW = 32 + 2 * R, BH = TH + (DYC - 1) * DIL;
+    constexpr int smem = (CC * TH * 32 + CC * BH * BW) * (int)sizeof(float);
+    static bool set = false;
+    if (!set && smem > 48 * 1024) {
+        PCFA_CUDA_TRY(cudaFuncSetAttribute(lc_fwd_tiled<D, DIL, DYC, TH, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set = true;
+    }
+    constexpr int NDYC = (D + DYC - 1) / DYC;
+    dim3 grid(ceil_div(g.oW, 32) * ceil_div(g.oH, TH), g.B * NDYC);
+    lc_fwd_tiled<D, DIL, DYC, TH, CC><<<grid, 8 * DYC * TH, smem, s>>>(in1, in2, out, g);
+    return after_launch();
+}
+
+template <int D, int DIL, int CPT>
+static int launch_lc_bwd_cpt(const float* in1, const float* in2, const float* gout, float* g1, float* g2,
+                             const LocalCorrGeom& g, cudaStream_t s) {
+    dim3 grid(ceil_div(g.iW, 32) * g.iH, g.B * ceil_div(g.C, 32 * CPT));
+    lc_bwd_rows<D, DIL, 1, CPT><<<grid, 256, 0, s>>>(in2, gout, g1, g);
+    PCFA_TRY(after_launch());
+    lc_bwd_rows<D, DIL, 2, CPT><<<grid, 256, 0, s>>>(in1, gout, g2, g);
+    return after_launch();
+}
+
+template <int D, int DIL>
+static int launch_lc_bwd(const float* in1, const float* in2, const float* gout, float* g1, float* g2,
+                         const LocalCorrGeom& g, cudaStream_t s) {
+    if (g.C >= 64 && g.C % 64 == 0) return launch_lc_bwd_cpt<D, DIL, 2>(in1, in2, gout, g1, g2, g, s);
+    return launch_lc_bwd_cpt<D, DIL, 1>(in1, in2, gout, g1, g2, g, s);
+}
+
 // ------------------------------------------------------------------ FlowNet2 backward, literal form
 // Follows correlation_cuda_kernel.cu:150-334 including the truncating integer divisions; used when
 // stride1 != 1 or kernel_size != 1 (for stride1 == 1, k == 1 it equals the fast path above).
@@ -278,8 +524,17 @@ static int scs_geom(LocalCorrGeom& g, int B, int C, int iH, int iW, const pcfa_s
     return PCFA_OK;
 }
 
+static bool tiled_ok(const LocalCorrGeom& g, int D, int DIL) {
+    return g.kH == 1 && g.kW == 1 && g.dH == 1 && g.dW == 1 && g.patchH == D && g.patchW == D && g.dpH == DIL &&
+           g.dpW == DIL && (int64_t)g.B * 7 <= 65535 && (int64_t)g.B * ceil_div(g.C, 32) <= 65535;
+}
+
 static int local_forward(const float* in1, const float* in2, float* out, const LocalCorrGeom& g,
                          cudaStream_t s) {
+    // the tiled kernel needs enough tiles to fill the machine; small maps (PWCNet levels 6..4) stay on the
+    // register-row kernel below, which parallelises over displacement rows instead
+    if (tiled_ok(g, 9, 1) && (int64_t)g.oH * g.oW >= 4096) return launch_lc_fwd<9, 1, 3, 4, 16>(in1, in2, out, g, s);   // PWCNet
+    if (tiled_ok(g, 21, 2) && (int64_t)g.oH * g.oW >= 2048) return launch_lc_fwd<21, 2, 3, 4, 16>(in1, in2, out, g, s); // FlowNet2
     if (g.kH == 1 && g.kW == 1 && g.patchW <= 21) {
         dim3 grid(ceil_div(g.oW, 32), g.oH, g.B * g.patchH), block(32, 4);
         if (g.patchW <= 9) local_corr_fwd_k1<9><<<grid, block, 0, s>>>(in1, in2, out, g);
@@ -293,6 +548,8 @@ static int local_forward(const float* in1, const float* in2, float* out, const L
 
 static int local_backward(const float* in1, const float* in2, const float* gout, float* g1, float* g2,
                           const LocalCorrGeom& g, cudaStream_t s) {
+    if (tiled_ok(g, 9, 1)) return launch_lc_bwd<9, 1>(in1, in2, gout, g1, g2, g, s);
+    if (tiled_ok(g, 21, 2)) return launch_lc_bwd<21, 2>(in1, in2, gout, g1, g2, g, s);
     const size_t smem = (size_t)g.patchH * g.patchW * 32 * sizeof(float);
     if (g.kH == 1 && g.kW == 1 && g.dH == 1 && g.dW == 1 && smem <= 200 * 1024 && g.iH <= 65535 &&
         g.B <= 65535) {
