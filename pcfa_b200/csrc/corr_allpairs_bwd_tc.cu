@@ -22,6 +22,7 @@
 // one per SM (a CTA finishes a block pair's partial sum with RED.ADD into zeroed outputs and moves on).
 #include "tc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace pcfa {
 
@@ -36,6 +37,7 @@ struct BwMaps {
 
 struct BwParams {
     int B, C, N, levels, pass, chunks_total, units_per_sample;
+    int terms, stages;                   // 2-CTA kernel: feature operand terms (1: TF32 hi, 2: hi + lo), ring depth
     long long work_total;                // B * units_per_sample * chunks_total  (linear (unit, K-chunk) space)
     int nl[BW_MAX_LEVELS];
     int chunk_off[BW_MAX_LEVELS + 1];    // pass I : K-chunk prefix over levels
@@ -213,7 +215,7 @@ corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P
 // across the pair (each CTA streams C/2 channel rows).  With two accumulators per CTA a pair owns FOUR row blocks
 // per streamed channel chunk: per MMA cycle each CTA streams 64 KB / 2048 cyc instead of 96 KB / 2048 cyc, and
 // the smaller stage makes room for a 3-deep ring.  Barrier protocol as in corr_pyramid_tc2_kernel.
-constexpr int BW2_STAGES = 3;
+constexpr int BW2_MAX_STAGES = 4;
 
 __device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, const BwParams& P, int rank) {
     BwSegment sg;
@@ -244,10 +246,11 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bh_bytes = (uint32_t)(P.C / 2) * 128u;               // this CTA's half of a [C x 32 tf32] tile
-    const uint32_t stage_bytes = 2 * BW_A_BYTES + 2 * bh_bytes;
-    const uint32_t bars = base + BW2_STAGES * stage_bytes;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW2_STAGES;
-    const uint32_t bar_accfull = bar_empty + 8 * BW2_STAGES, bar_accempty = bar_accfull + 8;
+    const uint32_t stage_bytes = 2 * BW_A_BYTES + (uint32_t)P.terms * bh_bytes;
+    const int nst = P.stages;
+    const uint32_t bars = base + nst * stage_bytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * BW2_MAX_STAGES;
+    const uint32_t bar_accfull = bar_empty + 8 * BW2_MAX_STAGES, bar_accempty = bar_accfull + 8;
     const uint32_t tmem_slot = bar_accempty + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -257,7 +260,7 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BW2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < nst; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_accfull, 1);
         mbar_init(bar_accempty, 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -293,7 +296,7 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
                     tma2_load_3d(dst, &maps.a[l], full, j0, sg.m0a, sg.b);
                     tma2_load_3d(dst + BW_A_BYTES, &maps.a[l], full, j0, sg.m0b, sg.b);
                     tma2_load_3d(dst + 2 * BW_A_BYTES, &maps.b[l], full, j0, crow, sg.b);
-                    tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[l], full, j0, crow, P.B + sg.b);
+                    if (P.terms == 2) tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[l], full, j0, crow, P.B + sg.b);
                 } else {
                     const int i0 = kc * BW_BK;
                     for (int g = 0; g < 4; ++g) {
@@ -301,9 +304,9 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
                         tma2_load_3d(dst + BW_A_BYTES + g * 4096, &maps.a[sg.level], full, sg.m0b + 32 * g, i0, sg.b);
                     }
                     tma2_load_3d(dst + 2 * BW_A_BYTES, &maps.b[0], full, i0, crow, sg.b);
-                    tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[0], full, i0, crow, P.B + sg.b);
+                    if (P.terms == 2) tma2_load_3d(dst + 2 * BW_A_BYTES + bh_bytes, &maps.b[0], full, i0, crow, P.B + sg.b);
                 }
-                if (++stage == BW2_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             w = sg.next;
         }
@@ -328,11 +331,11 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
                         const uint64_t ad = (P.pass == 1) ? umma_desc_sw128(sa + r * BW_A_BYTES + kk * 32)
                                                           : umma_desc_mn_tf32(sa + r * BW_A_BYTES + kk * 1024, 4096, 512);
                         tc2_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_hi + kk * 32), idesc, (kc != sg.k0) || (kk != 0));
-                        tc2_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_lo + kk * 32), idesc, 1);
+                        if (P.terms == 2) tc2_mma_tf32(d_tmem, ad, umma_desc_sw128(sb_lo + kk * 32), idesc, 1);
                     }
                 }
                 tc2_commit_mc(bar_empty + 8 * stage);
-                if (++stage == BW2_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             tc2_commit_mc(bar_accfull);
             accphase ^= 1;
@@ -374,19 +377,6 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     }
 }
 
-// src fp32 [n] * scale  ->  hi = round-to-nearest TF32 (low 13 bits zero), lo = v - hi (exact in fp32)
-__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
-                                  long long n, float scale) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = src[i] * scale;
-        uint32_t h;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float hf = __uint_as_float(h);
-        hi[i] = hf;
-        lo[i] = v - hf;
-    }
-}
-
 // Fused backward prep, one launch: TF32 hi/lo planes of alpha*fmap1 and of alpha*pool_l(fmap2) for every level
 // (successive 2x2 floor pooling), and zero-fill of every RED.ADD target (grad_fmap1, grad_fmap2, grad P_l).
 // CTA = 32 channels x (8 rows x 32 cols) of level 0; blockIdx.z selects (which fmap, sample, channel block).
@@ -395,7 +385,7 @@ struct BwPrepArgs {
     float* p_hi[BW_MAX_LEVELS]; long long p_plane[BW_MAX_LEVELS];   // [2][B][C][N_l]
     float* zero1; float* zero2; float* zero_gp[BW_MAX_LEVELS];     // grad_fmap1, grad_fmap2, grad P_l (l >= 1)
     int h[BW_MAX_LEVELS], w[BW_MAX_LEVELS];
-    int levels, B, C;
+    int levels, B, C, write_lo;
     float alpha;
 };
 __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
@@ -420,21 +410,34 @@ bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPre
     const int y = y0 + ty, x = x0 + tx;
     const bool inb = y < H && x < W;
     const long long hw = (long long)H * W;
+    const int nc = (a.C - c0) < 32 ? (a.C - c0) : 32;
     if (which == 0) {
-        for (int c = 0; c < 32 && c0 + c < a.C; ++c) {
-            if (!inb) continue;
-            const long long o = ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x;
-            float hi, lo;
-            tf32_split(__ldg(f1 + o) * a.alpha, &hi, &lo);
-            a.f1_hi[o] = hi;
-            a.f1_hi[a.f1_plane + o] = lo;
-            a.zero1[o] = 0.f;
-            a.zero2[o] = 0.f;
+        if (!inb) return;
+        const long long o0 = ((long long)b * a.C + c0) * hw + (long long)y * W + x;
+        for (int cb = 0; cb < nc; cb += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (cb + j < nc) ? __ldg(f1 + o0 + (cb + j) * hw) * a.alpha : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (cb + j >= nc) break;
+                const long long o = o0 + (cb + j) * hw;
+                float hi, lo;
+                tf32_split(v[j], &hi, &lo);
+                a.f1_hi[o] = hi;
+                if (a.write_lo) a.f1_hi[a.f1_plane + o] = lo;
+                a.zero1[o] = 0.f;
+                a.zero2[o] = 0.f;
+            }
         }
         return;
     }
-    for (int c = 0; c < 32; ++c)
-        t0[c][ty * 33 + tx] = (inb && c0 + c < a.C) ? __ldg(f2 + ((long long)b * a.C + c0 + c) * hw + (long long)y * W + x) * a.alpha : 0.f;
+    {
+        const long long o0 = ((long long)b * a.C + c0) * hw + (long long)y * W + x;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c)
+            t0[c][ty * 33 + tx] = (inb && c < nc) ? __ldg(f2 + o0 + c * hw) * a.alpha : 0.f;
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
         const int c = e / 64, r = (e / 16) % 4, q = e % 16;
@@ -464,22 +467,9 @@ bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPre
             float hi, lo;
             tf32_split(v, &hi, &lo);
             a.p_hi[l][o] = hi;
-            a.p_hi[l][a.p_plane[l] + o] = lo;
+            if (a.write_lo) a.p_hi[l][a.p_plane[l] + o] = lo;
             if (l > 0) a.zero_gp[l][o] = 0.f;
         }
-    }
-}
-
-__global__ void bw_avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int Hi, int Wi,
-                                   int Ho, int Wo) {
-    const long long total = R * Ho * Wo;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % Wo);
-        const int y = (int)((idx / Wo) % Ho);
-        const long long r = idx / ((long long)Wo * Ho);
-        const float* p = in + (r * Hi + 2 * y) * (long long)Wi + 2 * x;
-        out[idx] = 0.25f * ((p[0] + p[1]) + (p[Wi] + p[Wi + 1]));
     }
 }
 
@@ -547,12 +537,6 @@ static int enc3(EncodeTiledFn enc, CUtensorMap* m, const void* ptr, uint64_t d0,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? PCFA_OK : PCFA_E_BADARG;
 }
 
-static int grid1(long long total) {
-    long long b = (total + 255) / 256;
-    const long long cap = (long long)kNumSMs * 8;
-    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
-}
-
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
                              int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
     if (C % 32 != 0) two_cta = 0;                       // each CTA of a pair streams C/2 channel rows
@@ -563,12 +547,20 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
     const int N = H * W;
     const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
-    const float alpha = 1.0f / sqrtf((float)C);
+    // Feature operand terms.  The gradient pyramid enters the tensor core truncated to TF32 (relative error uniform in
+    // [0, 2^-10)), which dominates the result error; the lo term of the small operands then buys ~10 % accuracy for 2x
+    // the tensor work, so the CTA-pair kernel uses hi only.  The truncation's mean relative shrink (2^-11 / (2 ln 2)
+    // ... 2^-11 ln 2 for Benford ... uniform mantissas, ~3.5e-4) is folded into alpha, which leaves the zero-mean
+    // part of the error only: measured rel-L2 vs fp32 3.0e-4, below the 2-term result without it (4.1e-4).
+    static const int env_terms = [] { const char* e = getenv("PCFA_BWD_TERMS"); return e ? atoi(e) : 1; }();
+    static const int env_debias = [] { const char* e = getenv("PCFA_BWD_DEBIAS"); return e ? atoi(e) : 1; }();
+    const int terms = (two_cta && env_terms == 1) ? 1 : 2;
+    const float alpha = (1.0f / sqrtf((float)C)) * ((terms == 1 && env_debias) ? (1.0f + 3.5e-4f) : 1.0f);
 
     // ---- one launch: operand prep (alpha folded in, pooling, TF32 hi/lo split) + zero-fill of the RED.ADD targets
     {
         BwPrepArgs pa{};
-        pa.levels = levels; pa.B = B; pa.C = C; pa.alpha = alpha;
+        pa.levels = levels; pa.B = B; pa.C = C; pa.alpha = alpha; pa.write_lo = terms == 2;
         pa.f1_hi = reinterpret_cast<float*>(wsb + wl.f1_split);
         pa.f1_plane = (long long)B * C * N;
         pa.zero1 = gf1; pa.zero2 = gf2;
@@ -584,7 +576,10 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         PCFA_TRY(after_launch());
     }
 
-    const int smem = two_cta ? BW2_STAGES * (2 * BW_A_BYTES + C * 128) + 1024 + 256
+    const int stage2 = 2 * BW_A_BYTES + terms * (C / 2) * 128;
+    int stages2 = (227 * 1024 - 1024 - 256) / stage2;
+    if (stages2 > BW2_MAX_STAGES) stages2 = BW2_MAX_STAGES;
+    const int smem = two_cta ? stages2 * stage2 + 1024 + 256
                              : BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
     static int smem_set = 0, smem2_set = 0;
     if (!two_cta && smem > smem_set) {
@@ -613,7 +608,7 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     {
         BwMaps maps;
         BwParams P{};
-        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 1;
+        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 1; P.terms = terms; P.stages = stages2;
         int off = 0;
         for (int l = 0; l < levels; ++l) {
             const int nl = L.h[l] * L.w[l];
@@ -633,7 +628,7 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     {
         BwMaps maps;
         BwParams P{};
-        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 2;
+        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 2; P.terms = terms; P.stages = stages2;
         int off = 0;
         for (int l = 0; l < levels; ++l) {
             const int nl = L.h[l] * L.w[l];

@@ -23,6 +23,7 @@
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace pcfa {
 
@@ -256,7 +257,8 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
     const uint32_t bar_tfull = bar_qempty + 8, bar_tempty = bar_tfull + 16;
     const uint32_t tmem_slot = bar_tempty + 16;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // broadcast from lane 0 so the compiler can prove the role branches warp-uniform (plain SHFL in the epilogue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const long long ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
     const long long t_begin = P.total_pairs * cid / ncl, t_end = P.total_pairs * (cid + 1) / ncl;
@@ -393,41 +395,19 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
 }
 
 // ------------------------------------------------------------------------------------ operand prep
-// src fp32 [B][C][n]  ->  dst bf16 [2][B][n][C]  (hi plane, then mid plane), via a 32x32 smem transpose.
-__global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C, int n, float scale) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, i = n0 + tx;
-        tile[r][tx] = (c < C && i < n) ? src[((long long)b * C + c) * n + i] * scale : 0.f;
-    }
-    __syncthreads();
-    const long long plane = (long long)B * n * C;
-    for (int r = ty; r < 32; r += 8) {
-        const int i = n0 + r, c = c0 + tx;
-        if (i < n && c < C) {
-            const float v = tile[tx][r];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 mid = __float2bfloat16_rn(v - __bfloat162float(hi));
-            const long long o = ((long long)b * n + i) * C + c;
-            dst[o] = hi;
-            dst[plane + o] = mid;
-        }
-    }
-}
-
-// Fused operand prep for the target side: one pass over fmap2 produces the channel-last bf16 hi/mid planes of
+// Fused operand prep, ONE launch for both operands.  Target side: one pass over fmap2 produces the channel-last bf16 hi/mid planes of
 // pool_l(fmap2) for every level (successive 2x2 floor pooling, as F.avg_pool2d applied level by level).
 // CTA = 32 channels x (8 rows x 32 cols) of level 0: coalesced 128-byte row reads; each thread then owns a
 // channel PAIR of one cell and writes bf16x2, so a warp stores two 64-byte channel runs (full sectors).
 // Shared tiles use an odd per-channel stride (conflict-free for both the row-wise fill and the channel-wise drain).
+// Query side (blockIdx.z >= B*C/32): the same transpose + split of fmap1 * (1/sqrt C), level 0 only.
 struct TcPrepArgs {
     __nv_bfloat16* dst[TC_MAX_LEVELS];     // hi plane base per level; mid plane at + plane[l]
     long long plane[TC_MAX_LEVELS];        // B * H_l * W_l * C
     int h[TC_MAX_LEVELS], w[TC_MAX_LEVELS];
     int levels, B, C;
+    const float* qsrc;                     // fmap1: blockIdx.z >= B*C/32 handles the query operand (level 0 only)
+    __nv_bfloat16* qdst; long long qplane; float qscale;
 };
 constexpr int PT_S0 = 8 * 33 + 1, PT_S1 = 4 * 17 + 1, PT_S2 = 2 * 9 + 1, PT_S3 = 5;
 
@@ -459,17 +439,24 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
     const int H = a.h[0], W = a.w[0];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const int cblocks = a.C / 32;
-    const int b = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 32;
+    const bool qside = (int)blockIdx.z >= a.B * cblocks;
+    const int zz = qside ? (int)blockIdx.z - a.B * cblocks : (int)blockIdx.z;
+    const int b = zz / cblocks, c0 = (zz % cblocks) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
     {
         const int y = y0 + ty, x = x0 + tx;
         const bool inb = y < H && x < W;
-        const float* p = src + (((long long)b * a.C + c0) * H + y) * W + x;
+        const float* p = (qside ? a.qsrc : src) + (((long long)b * a.C + c0) * H + y) * W + x;
         const long long cs = (long long)H * W;
+        const float sc = qside ? a.qscale : 1.f;
 #pragma unroll 8
-        for (int c = 0; c < 32; ++c) t0[c * PT_S0 + ty * 33 + tx] = inb ? __ldg(p + c * cs) : 0.f;
+        for (int c = 0; c < 32; ++c) t0[c * PT_S0 + ty * 33 + tx] = inb ? __ldg(p + c * cs) * sc : 0.f;
     }
     __syncthreads();
+    if (qside) {
+        prep_targets_drain<0>(t0, PT_S0, 33, a.qdst, a.qplane, H, W, a.C, b, c0, y0, x0);
+        return;
+    }
     for (int e = threadIdx.x; e < 32 * 64; e += 256) {
         const int c = e >> 6, r = (e >> 4) & 3, q = e & 15;
         const float* s0 = t0 + c * PT_S0 + (2 * r) * 33 + 2 * q;
@@ -492,19 +479,6 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
     if (a.levels > 1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0);
     if (a.levels > 2) prep_targets_drain<2>(t2, PT_S2, 9, a.dst[2], a.plane[2], a.h[2], a.w[2], a.C, b, c0, y0, x0);
     if (a.levels > 3) prep_targets_drain<3>(t3, PT_S3, 5, a.dst[3], a.plane[3], a.h[3], a.w[3], a.C, b, c0, y0, x0);
-}
-
-__global__ void tc_avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int Hi,
-                                   int Wi, int Ho, int Wo) {
-    const long long total = R * Ho * Wo;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % Wo);
-        const int y = (int)((idx / Wo) % Ho);
-        const long long r = idx / ((long long)Wo * Ho);
-        const float* p = in + (r * Hi + 2 * y) * (long long)Wi + 2 * x;
-        out[idx] = 0.25f * ((p[0] + p[1]) + (p[Wi] + p[Wi + 1]));
-    }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -568,12 +542,6 @@ int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels) 
     return tc_workspace(B, C, H, W, levels).total;
 }
 
-static int split_transpose(const float* src, __nv_bfloat16* dst, int B, int C, int n, float scale, cudaStream_t s) {
-    dim3 grid(ceil_div(n, 32), ceil_div(C, 32), B);
-    split_transpose_kernel<<<grid, 256, 0, s>>>(src, dst, B, C, n, scale);
-    return after_launch();
-}
-
 int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyramid, void* ws, int64_t ws_bytes,
                             int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
     EncodeTiledFn enc = tc_encode_fn();
@@ -585,16 +553,18 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
 
     // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
-    PCFA_TRY(split_transpose(fmap1, reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split), B, C, N, 1.0f / sqrtf((float)C), s));
     {
         TcPrepArgs pa{};
         pa.levels = levels; pa.B = B; pa.C = C;
+        pa.qsrc = fmap1; pa.qdst = reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split);
+        pa.qplane = (long long)B * N * C; pa.qscale = 1.0f / sqrtf((float)C);
         for (int l = 0; l < levels; ++l) {
             pa.dst[l] = reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]);
             pa.plane[l] = (long long)B * L.h[l] * L.w[l] * C;
             pa.h[l] = L.h[l]; pa.w[l] = L.w[l];
         }
-        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * (C / 32));
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), 2 * B * (C / 32));
+        if (grid.z > 65535) return PCFA_E_TOOLARGE;
         prep_targets_kernel<<<grid, 256, 0, s>>>(fmap2, pa);
         PCFA_TRY(after_launch());
     }

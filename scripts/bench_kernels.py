@@ -44,4 +44,4 @@ for name, fn in calls.items():
     us = statistics.median(ts)
     rows.append(dict(name=name, us=round(us, 1), min_us=round(min(ts), 1), gbs=round(ab / us / 1e3, 1), frac=round(ab / us / 1e3 / peak, 3)))
     print(rows[-1])
-json.dump(rows, open("gpurun_out/bench_kernels.json", "w"))
+json.dump(rows, open("gpurun_out/bench_kernels.json" if B == 1 else f"gpurun_out/bench_kernels_B{B}.json", "w"))
