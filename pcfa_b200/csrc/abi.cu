@@ -19,3 +19,8 @@ extern "C" const char* pcfa_status_string(int status) {
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "pcfa: unknown status";
 }
+
+// Developer hook (not part of the ABI header): per-CTA globaltimer stamps of the backward tensor-core kernels are
+// written to `dev_ptr` (2 passes x 1024 CTAs x 8 u64) while it is non-null.  scripts/bwd_timeline.py reads them.
+namespace pcfa { void corr_pyramid_bwd_set_trace(void* p); }
+extern "C" void pcfa_debug_set_bwd_trace(void* dev_ptr) { pcfa::corr_pyramid_bwd_set_trace(dev_ptr); }

@@ -33,6 +33,7 @@ constexpr int BW_MAX_LEVELS = 4;
 struct BwMaps {
     CUtensorMap a[BW_MAX_LEVELS];    // G_l  [N_l, N, B]   pass I box {32,128,1} ; pass II box {32,32,1}
     CUtensorMap b[BW_MAX_LEVELS];    // pass I: split P_l [N_l, C, 2B] box {32,C,1} ; pass II: b[0] = split fmap1 [N, C, 2B]
+    CUtensorMap o[BW_MAX_LEVELS];    // 2-CTA kernel outputs [rows, C, B] box {128,16,1}: pass I o[0] = grad_fmap1 ; pass II grad P_l
 };
 
 struct BwParams {
@@ -43,6 +44,7 @@ struct BwParams {
     int chunk_off[BW_MAX_LEVELS + 1];    // pass I : K-chunk prefix over levels
     int unit_off[BW_MAX_LEVELS + 1];     // pass II: block-pair prefix over levels
     float* out[BW_MAX_LEVELS];           // pass I: out[0] = grad_fmap1 ; pass II: grad of P_l (out[0] = grad_fmap2)
+    unsigned long long* trace;           // optional per-CTA timeline (8 globaltimer stamps), set by pcfa_debug_set_trace
 };
 
 struct BwSegment { int b, level, rows_total, m0a, m0b, nblk, k0, k1; long long next; };
@@ -215,7 +217,11 @@ corr_pyramid_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams P
 // across the pair (each CTA streams C/2 channel rows).  With two accumulators per CTA a pair owns FOUR row blocks
 // per streamed channel chunk: per MMA cycle each CTA streams 64 KB / 2048 cyc instead of 96 KB / 2048 cyc, and
 // the smaller stage makes room for a 3-deep ring.  Barrier protocol as in corr_pyramid_tc2_kernel.
+__device__ __forceinline__ void bw_stamp(unsigned long long* tr, int slot) {
+    if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[(size_t)blockIdx.x * 8 + slot] = t; }
+}
 constexpr int BW2_MAX_STAGES = 4;
+constexpr int BW2_STG_BYTES = 32 * BW_BM * 4;     // epilogue staging tile for the bulk reduce-add
 
 __device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, const BwParams& P, int rank) {
     BwSegment sg;
@@ -248,7 +254,8 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     const uint32_t bh_bytes = (uint32_t)(P.C / 2) * 128u;               // this CTA's half of a [C x 32 tf32] tile
     const uint32_t stage_bytes = 2 * BW_A_BYTES + (uint32_t)P.terms * bh_bytes;
     const int nst = P.stages;
-    const uint32_t bars = base + nst * stage_bytes;
+    const uint32_t stg = base + nst * stage_bytes;                      // 2 x [32 channels][128 rows] fp32 staging tiles
+    const uint32_t bars = stg + 2 * BW2_STG_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * BW2_MAX_STAGES;
     const uint32_t bar_accfull = bar_empty + 8 * BW2_MAX_STAGES, bar_accempty = bar_accfull + 8;
     const uint32_t tmem_slot = bar_accempty + 8;
@@ -259,6 +266,7 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
 
+    if (threadIdx.x == 0) bw_stamp(P.trace, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_accfull, 1);
@@ -275,6 +283,7 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) bw_stamp(P.trace, 1);
 
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer (both CTAs)
@@ -322,6 +331,7 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
             for (int kc = sg.k0; kc < sg.k1; ++kc) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
+                if (w == w_begin && kc == sg.k0) bw_stamp(P.trace, 2);
                 const uint32_t sa = base + stage * stage_bytes, sb_hi = sa + 2 * BW_A_BYTES, sb_lo = sb_hi + bh_bytes;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -341,36 +351,65 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
             accphase ^= 1;
             w = sg.next;
         }
+        bw_stamp(P.trace, 3);
     } else if (warp >= 4) {
         // ===================================================================== epilogue (per segment, both CTAs)
+        // The SM issues REDs at ~1.3 cycles per lane (64 K lanes per CTA and segment would cost ~45 us, fully exposed
+        // at the end of the pass).  Instead the four warps of a row block stage [16 channels][128 rows] half tiles in shared
+        // memory (lanes = consecutive rows: conflict-free) and one thread issues a bulk tensor reduce-add; rows past
+        // the end of the tensor are clipped by the TMA unit.
         const int ew = warp & 3, r = (warp - 4) >> 2;
-        uint32_t accphase = 0;
+        const uint32_t my_stg = stg + r * BW2_STG_BYTES;
+        const bool issuer = (ew == 0 && lane == 0);
+        uint32_t accphase = 0, gg = 0;
         for (long long w = w_begin; w < w_end;) {
             const BwSegment sg = bw2_segment(w, w_end, P, rank);
             mbar_wait(bar_accfull, accphase);
             tc_fence_after();
-            const int m = (r == 0 ? sg.m0a : sg.m0b) + ew * 32 + lane;
-            float* out = P.out[(P.pass == 1) ? 0 : sg.level] + (long long)sg.b * P.C * sg.rows_total + m;
+            if (warp == 4 && lane == 0) bw_stamp(P.trace, sg.next >= w_end ? 5 : 4);
+            const int m0 = (r == 0 ? sg.m0a : sg.m0b);
+            const bool live = m0 < sg.rows_total;                        // uniform over the four warps of this block
+            const CUtensorMap* omap = &maps.o[(P.pass == 1) ? 0 : sg.level];
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + r * P.C;
             for (int c0 = 0; c0 < P.C; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(taddr + c0, v);
                 tc_wait_ld();
-                if (m < sg.rows_total) {
+                if (c0 + 32 >= P.C) {                                   // accumulator fully read: release it to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta0(bar_accempty);
+                }
+                if (live) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < P.C) red_add(out + (long long)(c0 + j) * sg.rows_total, __uint_as_float(v[j]));
+                    for (int h = 0; h < 2; ++h) {                       // two 16-channel half tiles, double-buffered
+                        const uint32_t buf = my_stg + h * (BW2_STG_BYTES / 2);
+                        if (gg >= 2) {
+                            if (issuer) tma_wait_group_read1();         // the reduction that last used `buf` has read it
+                            named_bar_sync(1 + r, 128);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(buf + (uint32_t)((j * BW_BM + ew * 32 + lane) * 4)), "r"(v[16 * h + j]) : "memory");
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + r, 128);
+                        if (issuer) {
+                            tma_reduce_add_3d(omap, buf, m0, c0 + 16 * h, sg.b);
+                            tma_commit_group();
+                        }
+                        ++gg;
+                    }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cta0(bar_accempty);
             accphase ^= 1;
             w = sg.next;
         }
+        if (issuer) tma_wait_group0();                                   // all reductions performed before the CTA exits
+        if (warp == 4 && lane == 0) bw_stamp(P.trace, 6);
     }
     tc_fence_before();
     cluster_sync_all();
+    if (threadIdx.x == 0) bw_stamp(P.trace, 7);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
@@ -394,103 +433,143 @@ __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
     *hi = __uint_as_float(h);
     *lo = v - *hi;
 }
+constexpr int BP_CH = 8;        // channels per CTA of the pooled path: 4x the CTAs of a 32-channel tile, all loads in flight
+template <int LVL>
+__device__ __forceinline__ void bw_prep_drain(const float* __restrict__ t, int cstride, int rstride, const BwPrepArgs& a,
+                                              int b, int c0, int nc, int y0, int x0) {
+    constexpr int ww = 32 >> LVL, cells = (8 >> LVL) * ww;
+    const int Hl = a.h[LVL], Wl = a.w[LVL];
+    for (int e = threadIdx.x; e < BP_CH * cells; e += 256) {
+        const int c = e / cells, cell = e % cells, r = cell / ww, q = cell % ww;      // powers of two: shifts
+        const int yy = (y0 >> LVL) + r, xx = (x0 >> LVL) + q;
+        if (yy >= Hl || xx >= Wl || c >= nc) continue;
+        const long long o = (((long long)b * a.C + c0 + c) * Hl + yy) * Wl + xx;
+        float hi, lo;
+        tf32_split(t[c * cstride + r * rstride + q], &hi, &lo);
+        a.p_hi[LVL][o] = hi;
+        if (a.write_lo) a.p_hi[LVL][a.p_plane[LVL] + o] = lo;
+        if (LVL > 0) a.zero_gp[LVL][o] = 0.f;
+    }
+}
+
+// blockIdx.x < flat_blocks: elementwise part (fmap1 -> TF32 planes, zero-fill of grad_fmap1 / grad_fmap2), 4 elements
+// per thread (128-bit accesses when `vec`).  Remaining CTAs: BP_CH channels x (8 rows x 32 cols) of fmap2, pooled.
 __global__ void __launch_bounds__(256)
-bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, BwPrepArgs a) {
-    __shared__ float t0[32][8 * 33 + 1];     // odd per-channel strides: conflict-free fills and drains
-    __shared__ float t1[32][4 * 17 + 1];
-    __shared__ float t2[32][2 * 9 + 1];
-    __shared__ float t3[32][5];
+bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const BwPrepArgs a, int flat_blocks, int vec,
+               int nx, int ny) {
     const int H = a.h[0], W = a.w[0];
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    const int cblocks = ceil_div(a.C, 32);
-    const int which = blockIdx.z / (a.B * cblocks);                  // 0: fmap1, 1: fmap2
-    const int rem = blockIdx.z % (a.B * cblocks);
-    const int b = rem / cblocks, c0 = (rem % cblocks) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int y = y0 + ty, x = x0 + tx;
-    const bool inb = y < H && x < W;
     const long long hw = (long long)H * W;
-    const int nc = (a.C - c0) < 32 ? (a.C - c0) : 32;
-    if (which == 0) {
-        if (!inb) return;
-        const long long o0 = ((long long)b * a.C + c0) * hw + (long long)y * W + x;
-        for (int cb = 0; cb < nc; cb += 8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (cb + j < nc) ? __ldg(f1 + o0 + (cb + j) * hw) * a.alpha : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (cb + j >= nc) break;
-                const long long o = o0 + (cb + j) * hw;
+    if ((int)blockIdx.x < flat_blocks) {
+        const long long n = (long long)a.B * a.C * hw;
+        const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+        if (i >= n) return;
+        if (vec) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(f1 + i));
+            float4 h, l;
+            tf32_split(v.x * a.alpha, &h.x, &l.x); tf32_split(v.y * a.alpha, &h.y, &l.y);
+            tf32_split(v.z * a.alpha, &h.z, &l.z); tf32_split(v.w * a.alpha, &h.w, &l.w);
+            *reinterpret_cast<float4*>(a.f1_hi + i) = h;
+            if (a.write_lo) *reinterpret_cast<float4*>(a.f1_hi + a.f1_plane + i) = l;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a.zero1 + i) = z;
+            *reinterpret_cast<float4*>(a.zero2 + i) = z;
+        } else {
+            for (long long k = i; k < i + 4 && k < n; ++k) {
                 float hi, lo;
-                tf32_split(v[j], &hi, &lo);
-                a.f1_hi[o] = hi;
-                if (a.write_lo) a.f1_hi[a.f1_plane + o] = lo;
-                a.zero1[o] = 0.f;
-                a.zero2[o] = 0.f;
+                tf32_split(__ldg(f1 + k) * a.alpha, &hi, &lo);
+                a.f1_hi[k] = hi;
+                if (a.write_lo) a.f1_hi[a.f1_plane + k] = lo;
+                a.zero1[k] = 0.f;
+                a.zero2[k] = 0.f;
             }
         }
         return;
     }
+    __shared__ float t0[BP_CH * (8 * 33 + 1)];       // odd per-channel strides: conflict-free fills and drains
+    __shared__ float t1[BP_CH * (4 * 17 + 1)];
+    __shared__ float t2[BP_CH * (2 * 9 + 1)];
+    __shared__ float t3[BP_CH * 5];
+    constexpr int S0 = 8 * 33 + 1, S1 = 4 * 17 + 1, S2 = 2 * 9 + 1, S3 = 5;
+    int pb = (int)blockIdx.x - flat_blocks;
+    const int x0 = (pb % nx) * 32; pb /= nx;
+    const int y0 = (pb % ny) * 8; pb /= ny;
+    const int cblocks = ceil_div(a.C, BP_CH);
+    const int b = pb / cblocks, c0 = (pb % cblocks) * BP_CH;
+    const int nc = (a.C - c0) < BP_CH ? (a.C - c0) : BP_CH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     {
-        const long long o0 = ((long long)b * a.C + c0) * hw + (long long)y * W + x;
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c)
-            t0[c][ty * 33 + tx] = (inb && c < nc) ? __ldg(f2 + o0 + c * hw) * a.alpha : 0.f;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool inb = y < H && x < W;
+        const float* p = f2 + ((long long)b * a.C + c0) * hw + (long long)y * W + x;
+        float v[BP_CH];
+#pragma unroll
+        for (int c = 0; c < BP_CH; ++c) v[c] = (inb && c < nc) ? __ldg(p + c * hw) * a.alpha : 0.f;
+#pragma unroll
+        for (int c = 0; c < BP_CH; ++c) t0[c * S0 + ty * 33 + tx] = v[c];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 4 * 16; e += 256) {
-        const int c = e / 64, r = (e / 16) % 4, q = e % 16;
-        t1[c][r * 17 + q] = 0.25f * ((t0[c][(2 * r) * 33 + 2 * q] + t0[c][(2 * r) * 33 + 2 * q + 1]) + (t0[c][(2 * r + 1) * 33 + 2 * q] + t0[c][(2 * r + 1) * 33 + 2 * q + 1]));
+    for (int e = threadIdx.x; e < BP_CH * 64; e += 256) {
+        const int c = e >> 6, r = (e >> 4) & 3, q = e & 15;
+        const float* s0 = t0 + c * S0 + (2 * r) * 33 + 2 * q;
+        t1[c * S1 + r * 17 + q] = 0.25f * ((s0[0] + s0[1]) + (s0[33] + s0[34]));
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * 2 * 8; e += 256) {
-        const int c = e / 16, r = (e / 8) % 2, q = e % 8;
-        t2[c][r * 9 + q] = 0.25f * ((t1[c][(2 * r) * 17 + 2 * q] + t1[c][(2 * r) * 17 + 2 * q + 1]) + (t1[c][(2 * r + 1) * 17 + 2 * q] + t1[c][(2 * r + 1) * 17 + 2 * q + 1]));
+    if (threadIdx.x < BP_CH * 16) {
+        const int e = threadIdx.x, c = e >> 4, r = (e >> 3) & 1, q = e & 7;
+        const float* s1 = t1 + c * S1 + (2 * r) * 17 + 2 * q;
+        t2[c * S2 + r * 9 + q] = 0.25f * ((s1[0] + s1[1]) + (s1[17] + s1[18]));
     }
     __syncthreads();
-    if (threadIdx.x < 32 * 4) {
-        const int c = threadIdx.x / 4, q = threadIdx.x % 4;
-        t3[c][q] = 0.25f * ((t2[c][2 * q] + t2[c][2 * q + 1]) + (t2[c][9 + 2 * q] + t2[c][9 + 2 * q + 1]));
+    if (threadIdx.x < BP_CH * 4) {
+        const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const float* s2 = t2 + c * S2 + 2 * q;
+        t3[c * S3 + q] = 0.25f * ((s2[0] + s2[1]) + (s2[9] + s2[10]));
     }
     __syncthreads();
-    for (int l = 0; l < a.levels; ++l) {
-        const int hh = 8 >> l, ww = 32 >> l, cells = hh * ww;
-        const int Hl = a.h[l], Wl = a.w[l];
-        for (int e = threadIdx.x; e < 32 * cells; e += 256) {
-            const int c = e / cells, cell = e - c * cells;
-            const int r = cell / ww, q = cell - r * ww;
-            const int yy = (y0 >> l) + r, xx = (x0 >> l) + q;
-            if (yy >= Hl || xx >= Wl || c0 + c >= a.C) continue;
-            const float v = (l == 0) ? t0[c][r * 33 + q] : (l == 1) ? t1[c][r * 17 + q] : (l == 2) ? t2[c][r * 9 + q] : t3[c][q];
-            const long long o = (((long long)b * a.C + c0 + c) * Hl + yy) * Wl + xx;
-            float hi, lo;
-            tf32_split(v, &hi, &lo);
-            a.p_hi[l][o] = hi;
-            if (a.write_lo) a.p_hi[l][a.p_plane[l] + o] = lo;
-            if (l > 0) a.zero_gp[l][o] = 0.f;
-        }
-    }
+    bw_prep_drain<0>(t0, S0, 33, a, b, c0, nc, y0, x0);
+    if (a.levels > 1) bw_prep_drain<1>(t1, S1, 17, a, b, c0, nc, y0, x0);
+    if (a.levels > 2) bw_prep_drain<2>(t2, S2, 9, a, b, c0, nc, y0, x0);
+    if (a.levels > 3) bw_prep_drain<3>(t3, S3, 5, a, b, c0, nc, y0, x0);
 }
 
 // grad_fmap2[r, y, x] += sum_{l>=1} gP_l[r, y>>l, x>>l] * 0.25^l   (adjoint of the successive floor pooling).
 // grid: (ceil(W/128), H, R) with 128 threads: no index divisions, coalesced rows.
 struct BwUnpool { const float* g[BW_MAX_LEVELS]; int h[BW_MAX_LEVELS], w[BW_MAX_LEVELS]; int levels; };
-__global__ void __launch_bounds__(128)
-bw_unpool_kernel(float* __restrict__ gf2, const BwUnpool a, int H, int W) {
-    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
-    const long long r = blockIdx.z;
-    if (x >= W) return;
-    const long long idx = (r * H + y) * W + x;
-    float acc = gf2[idx], sc = 1.f;
+// CTA = (plane r, 8 rows); thread = 4 consecutive x of one row (128-bit accesses when W % 4 == 0): no index divisions.
+__global__ void __launch_bounds__(256)
+bw_unpool_kernel(float* __restrict__ gf2, const BwUnpool a, int H, int W, int vec) {
+    const long long r = blockIdx.y;
+    const int xq = ceil_div(W, 4);                       // 4-wide column groups per row
+    for (int item = threadIdx.x; item < 8 * xq; item += 256) {
+        const int y = blockIdx.x * 8 + item / xq, x = (item % xq) * 4;
+        if (y >= H) break;
+        float* p = gf2 + (r * H + y) * W + x;
+        float v[4];
+        if (vec) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else {
 #pragma unroll
-    for (int l = 1; l < BW_MAX_LEVELS; ++l) {
-        if (l >= a.levels) break;
-        sc *= 0.25f;
-        const int yy = y >> l, xx = x >> l;
-        if (yy < a.h[l] && xx < a.w[l]) acc = fmaf(sc, __ldg(a.g[l] + (r * a.h[l] + yy) * a.w[l] + xx), acc);
+            for (int k = 0; k < 4; ++k) v[k] = (x + k < W) ? p[k] : 0.f;
+        }
+        float sc = 1.f;
+#pragma unroll
+        for (int l = 1; l < BW_MAX_LEVELS; ++l) {
+            if (l >= a.levels) break;
+            sc *= 0.25f;
+            const int yy = y >> l;
+            if (yy >= a.h[l]) continue;
+            const float* gl = a.g[l] + (r * a.h[l] + yy) * a.w[l];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xx = (x + k) >> l;
+                if (xx < a.w[l]) v[k] = fmaf(sc, __ldg(gl + xx), v[k]);
+            }
+        }
+        if (vec) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (x + k < W) p[k] = v[k];
+        }
     }
-    gf2[idx] = acc;
 }
 
 struct BwWorkspace { int64_t f1_split, p_split[BW_MAX_LEVELS], pooled[BW_MAX_LEVELS], gp[BW_MAX_LEVELS], total; };
@@ -537,6 +616,9 @@ static int enc3(EncodeTiledFn enc, CUtensorMap* m, const void* ptr, uint64_t d0,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? PCFA_OK : PCFA_E_BADARG;
 }
 
+static unsigned long long* g_bw_trace = nullptr;
+void corr_pyramid_bwd_set_trace(void* p) { g_bw_trace = reinterpret_cast<unsigned long long*>(p); }
+
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
                              int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
     if (C % 32 != 0) two_cta = 0;                       // each CTA of a pair streams C/2 channel rows
@@ -570,16 +652,22 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
             pa.zero_gp[l] = (l == 0) ? nullptr : reinterpret_cast<float*>(wsb + wl.gp[l]);
             pa.h[l] = L.h[l]; pa.w[l] = L.w[l];
         }
-        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), 2 * B * ceil_div(C, 32));
-        if (grid.z > 65535) return PCFA_E_TOOLARGE;
-        bw_prep_kernel<<<grid, 256, 0, s>>>(f1, f2, pa);
+        const long long n = (long long)B * C * N;
+        const long long flat_blocks = (n + 1023) / 1024;
+        const int nx = ceil_div(W, 32), ny = ceil_div(H, 8);
+        const long long pooled_blocks = (long long)nx * ny * B * ceil_div(C, BP_CH);
+        if (flat_blocks + pooled_blocks > 0x7fffffffLL) return PCFA_E_TOOLARGE;
+        const uintptr_t al = reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(gf1) |
+                             reinterpret_cast<uintptr_t>(gf2) | reinterpret_cast<uintptr_t>(pa.f1_hi);
+        const int vec = ((al & 15) == 0 && n % 4 == 0 && pa.f1_plane % 4 == 0) ? 1 : 0;
+        bw_prep_kernel<<<(unsigned)(flat_blocks + pooled_blocks), 256, 0, s>>>(f1, f2, pa, (int)flat_blocks, vec, nx, ny);
         PCFA_TRY(after_launch());
     }
 
     const int stage2 = 2 * BW_A_BYTES + terms * (C / 2) * 128;
-    int stages2 = (227 * 1024 - 1024 - 256) / stage2;
+    int stages2 = (227 * 1024 - 1024 - 256 - 2 * BW2_STG_BYTES) / stage2;
     if (stages2 > BW2_MAX_STAGES) stages2 = BW2_MAX_STAGES;
-    const int smem = two_cta ? stages2 * stage2 + 1024 + 256
+    const int smem = two_cta ? stages2 * stage2 + 2 * BW2_STG_BYTES + 1024 + 256
                              : BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
     static int smem_set = 0, smem2_set = 0;
     if (!two_cta && smem > smem_set) {
@@ -606,9 +694,9 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
 
     // ---- pass I: grad_fmap1
     {
-        BwMaps maps;
+        BwMaps maps{};
         BwParams P{};
-        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 1; P.terms = terms; P.stages = stages2;
+        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 1; P.terms = terms; P.stages = stages2; P.trace = g_bw_trace;
         int off = 0;
         for (int l = 0; l < levels; ++l) {
             const int nl = L.h[l] * L.w[l];
@@ -622,23 +710,26 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         P.units_per_sample = ceil_div(ceil_div(N, BW_BM), group);
         P.work_total = (long long)B * P.units_per_sample * P.chunks_total;
         P.out[0] = gf1;
+        if (two_cta) PCFA_TRY(enc3(enc, &maps.o[0], gf1, N, C, B, BW_BM, 16, CU_TENSOR_MAP_SWIZZLE_NONE));
+        for (int l = 1; l < BW_MAX_LEVELS; ++l) maps.o[l] = maps.o[0];
         PCFA_TRY(launch(maps, P));
     }
     // ---- pass II: grad of P_l (level 0 goes straight into grad_fmap2)
     {
-        BwMaps maps;
+        BwMaps maps{};
         BwParams P{};
-        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 2; P.terms = terms; P.stages = stages2;
+        P.B = B; P.C = C; P.N = N; P.levels = levels; P.pass = 2; P.terms = terms; P.stages = stages2; P.trace = g_bw_trace ? g_bw_trace + 8 * 1024 : nullptr;
         int off = 0;
         for (int l = 0; l < levels; ++l) {
             const int nl = L.h[l] * L.w[l];
             P.nl[l] = nl; P.unit_off[l] = off; off += ceil_div(ceil_div(nl, BW_BM), group);
             PCFA_TRY(enc3(enc, &maps.a[l], gpyr + L.off[l], nl, N, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
             P.out[l] = (l == 0) ? gf2 : reinterpret_cast<float*>(wsb + wl.gp[l]);
+            if (two_cta) PCFA_TRY(enc3(enc, &maps.o[l], P.out[l], nl, C, B, BW_BM, 16, CU_TENSOR_MAP_SWIZZLE_NONE));
         }
         for (int l = levels; l <= BW_MAX_LEVELS; ++l) P.unit_off[l] = off;
         PCFA_TRY(enc3(enc, &maps.b[0], wsb + wl.f1_split, N, C, 2 * B, BW_BK, two_cta ? C / 2 : C));
-        for (int l = levels; l < BW_MAX_LEVELS; ++l) maps.a[l] = maps.a[0];
+        for (int l = levels; l < BW_MAX_LEVELS; ++l) { maps.a[l] = maps.a[0]; maps.o[l] = maps.o[0]; }
         for (int l = 1; l < BW_MAX_LEVELS; ++l) maps.b[l] = maps.b[0];
         P.chunks_total = ceil_div(N, BW_BK);
         P.units_per_sample = off;
@@ -652,9 +743,10 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
             u.g[l] = (l == 0) ? gf2 : reinterpret_cast<const float*>(wsb + wl.gp[l]);
             u.h[l] = L.h[l]; u.w[l] = L.w[l];
         }
-        dim3 ugrid(ceil_div(W, 128), H, B * C);
-        if (ugrid.z > 65535 || H > 65535) return PCFA_E_TOOLARGE;
-        bw_unpool_kernel<<<ugrid, 128, 0, s>>>(gf2, u, H, W);
+        dim3 ugrid(ceil_div(H, 8), B * C);
+        if (ugrid.y > 65535) return PCFA_E_TOOLARGE;
+        const int vec = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(gf2) & 15) == 0) ? 1 : 0;
+        bw_unpool_kernel<<<ugrid, 256, 0, s>>>(gf2, u, H, W, vec);
         PCFA_TRY(after_launch());
     }
     return PCFA_OK;

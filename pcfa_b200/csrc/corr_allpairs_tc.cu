@@ -449,8 +449,11 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
         const float* p = (qside ? a.qsrc : src) + (((long long)b * a.C + c0) * H + y) * W + x;
         const long long cs = (long long)H * W;
         const float sc = qside ? a.qscale : 1.f;
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) t0[c * PT_S0 + ty * 33 + tx] = inb ? __ldg(p + c * cs) * sc : 0.f;
+        float v[32];                                                  // all 32 loads in flight
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = inb ? __ldg(p + c * cs) * sc : 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) t0[c * PT_S0 + ty * 33 + tx] = v[c];
     }
     __syncthreads();
     if (qside) {
