@@ -48,7 +48,9 @@ def test_corrblock_matches_reference_outputs(golden, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("shape,levels,radius", [((2, 32, 18, 27), 4, 4), ((1, 64, 9, 17), 3, 3),
-                                                 ((3, 16, 8, 8), 2, 4), ((1, 128, 23, 40), 4, 4)])
+                                                 ((3, 16, 8, 8), 2, 4), ((1, 128, 23, 40), 4, 4),
+                                                 # every level width % 4 == 0: the 128-bit lookup kernels
+                                                 ((1, 32, 16, 32), 4, 4), ((2, 16, 12, 16), 3, 3), ((1, 16, 17, 48), 3, 4)])
 def test_corrblock_vs_oracle_ragged_shapes(shape, levels, radius):
     from oracle import ops as O
     from pcfa_b200.corr_block import CorrBlock
