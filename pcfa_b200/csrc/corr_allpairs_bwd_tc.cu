@@ -266,6 +266,9 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
 
+    // Programmatic dependent launch: pass II does not read pass I's output, so its CTAs may take over an SM as soon as
+    // the pass-I CTA there has exited (the tail of one pass overlaps the head of the next).  No-op without a dependent.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) bw_stamp(P.trace, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -680,11 +683,19 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     }
     const int sms = tc_num_sms();
     const int group = two_cta ? 4 : 2;                  // row blocks per work unit
+    static const int env_pdl = [] { const char* e = getenv("PCFA_BWD_PDL"); return e ? atoi(e) : 1; }();
     auto launch = [&](const BwMaps& maps, const BwParams& P) -> int {
         if (two_cta) {
             long long clusters = sms / 2;
             if (clusters > P.work_total) clusters = P.work_total;
-            corr_pyramid_bwd_tc2_kernel<<<(int)(2 * clusters), BW_THREADS, smem, s>>>(maps, P);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(BW_THREADS);
+            cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = (P.pass == 2 && env_pdl) ? 1 : 0;      // pass II may overlap pass I's tail
+            PCFA_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_pyramid_bwd_tc2_kernel, maps, P));
         } else {
             const int grid = (int)(P.work_total < sms ? P.work_total : sms);
             corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);

@@ -282,6 +282,8 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
 
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer (both CTAs)
+        // launched as a programmatic dependent of the operand-prep kernel: everything above overlapped its tail
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         int stage = 0; uint32_t phase = 0, qphase = 0;
         long long cur = -1;
         for (long long t = t_begin; t < t_end; ++t) {
@@ -438,6 +440,7 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
     __shared__ float t3[32 * PT_S3];
     const int H = a.h[0], W = a.w[0];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the pyramid kernel's prologue may start now
     const int cblocks = a.C / 32;
     const bool qside = (int)blockIdx.z >= a.B * cblocks;
     const int zz = qside ? (int)blockIdx.z - a.B * cblocks : (int)blockIdx.z;
@@ -618,7 +621,15 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
         }
         long long clusters = tc_num_sms() / 2;
         if (clusters > P.total_pairs) clusters = P.total_pairs;
-        corr_pyramid_tc2_kernel<<<(int)(2 * clusters), TC_THREADS, smem, s>>>(maps, P, pyramid);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        static const int env_pdl = [] { const char* e = getenv("PCFA_FWD_PDL"); return e ? atoi(e) : 1; }();
+        cfg.attrs = at; cfg.numAttrs = env_pdl ? 1 : 0;
+        PCFA_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_pyramid_tc2_kernel, maps, P, pyramid));
         return after_launch();
     }
     static bool attr_set = false;

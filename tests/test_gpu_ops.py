@@ -10,6 +10,10 @@ pytestmark = pytest.mark.gpu
 
 TOL = dict(rtol=1e-3, atol_rms=1e-3)       # BASELINE.json: rtol 1e-3 on fp32 cost volumes and flows
 TIGHT = dict(rtol=1e-4, atol_rms=1e-4)
+# Gradients through the tensor-core backward: the gradient pyramid enters the MMA truncated to TF32 (2^-11 per element,
+# rel-L2 3e-4 on the result, scripts/bwd_precision.py), so the element-wise maximum over ~1e4-1e6 entries reaches
+# ~4.5 sigma = 1.5e-3 rms.  The fp32 SIMT backward (PCFA_CORR_IMPL=1) is tested at TOL against the same oracle.
+GTOL = dict(rtol=1e-3, atol_rms=4e-3)
 
 
 def cu(a, grad=False):
@@ -70,8 +74,28 @@ def test_corrblock_vs_oracle_ragged_shapes(shape, levels, radius):
     (out * cu(go)).sum().backward()
     gp = O.corr_lookup_backward(go, coords, levels, radius)
     g1, g2 = O.corr_pyramid_backward(gp, f1, f2, levels)
-    assert_close(npy(t1.grad), g1, what="g fmap1", **TOL)
-    assert_close(npy(t2.grad), g2, what="g fmap2", **TOL)
+    assert_close(npy(t1.grad), g1, what="g fmap1", **GTOL)
+    assert_close(npy(t2.grad), g2, what="g fmap2", **GTOL)
+
+
+def test_corrblock_fp32_backward_vs_oracle(monkeypatch):
+    """The exact-fp32 SIMT build/backward (impl 1) against the oracle at the cost-volume tolerance."""
+    from oracle import ops as O
+    from pcfa_b200.corr_block import CorrBlock
+    monkeypatch.setenv("PCFA_CORR_IMPL", "1")
+    g = np.random.default_rng(5)
+    B, C, H, W = 1, 32, 16, 32
+    f1 = g.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = g.standard_normal((B, C, H, W)).astype(np.float32)
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    coords = (np.stack([xs, ys])[None] + 4 * g.standard_normal((B, 2, H, W))).astype(np.float32)
+    t1, t2 = cu(f1, True), cu(f2, True)
+    out = CorrBlock(t1, t2, num_levels=4, radius=4)(cu(coords))
+    go = g.standard_normal(out.shape).astype(np.float32)
+    (out * cu(go)).sum().backward()
+    g1, g2 = O.corr_pyramid_backward(O.corr_lookup_backward(go, coords, 4, 4), f1, f2, 4)
+    assert_close(npy(t1.grad), g1, what="g fmap1 (fp32)", **TOL)
+    assert_close(npy(t2.grad), g2, what="g fmap2 (fp32)", **TOL)
 
 
 def test_corr_static_and_forward_only():
