@@ -12,6 +12,7 @@ lib = _lib.load()
 B, C, H, W, L, R = int(sys.argv[1]) if len(sys.argv) > 1 else 1, 256, 55, 128, 4, 4
 impl = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 reps = 15
+noflush = len(sys.argv) > 3 and sys.argv[3] == 'noflush'   # warm-L2 variant: what the kernel does when its inputs are L2-resident
 g = torch.Generator().manual_seed(0)
 f1 = torch.randn(B, C, H, W, generator=g).cuda(); f2 = torch.randn(B, C, H, W, generator=g).cuda()
 ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
@@ -35,7 +36,7 @@ rows = []
 for name, fn in calls.items():
     ts = []
     for i in range(reps + 3):
-        flush.zero_()
+        if not noflush: flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); st = fn(); e1.record(); torch.cuda.synchronize()
         assert st == 0, (name, st)
@@ -44,4 +45,4 @@ for name, fn in calls.items():
     us = statistics.median(ts)
     rows.append(dict(name=name, us=round(us, 1), min_us=round(min(ts), 1), gbs=round(ab / us / 1e3, 1), frac=round(ab / us / 1e3 / peak, 3)))
     print(rows[-1])
-json.dump(rows, open("gpurun_out/bench_kernels.json" if B == 1 else f"gpurun_out/bench_kernels_B{B}.json", "w"))
+json.dump(rows, open(("gpurun_out/bench_kernels.json" if B == 1 else f"gpurun_out/bench_kernels_B{B}.json") if not noflush else f"gpurun_out/bench_kernels_B{B}_warm.json", "w"))
