@@ -31,6 +31,7 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
 constexpr int TC_PH = 8, TC_PW = 16;          // target patch
 constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 384;             // 4 control warps + 8 epilogue warps
+constexpr int TC2_THREADS = 640;            // CTA-pair kernel: 4 control warps + 16 epilogue warps (lane quarter x column quarter)
 constexpr int TC_TILE_BYTES = 128 * 128;      // one [128 rows x 64 bf16] SW128 tile
 constexpr int TC_MAX_KCHUNKS = 4;             // C <= 256
 constexpr int TC_MAX_LEVELS = 4;
@@ -48,6 +49,7 @@ struct TcParams {
     float scale;
     // 2-CTA variant: work item = (sample, pair of query blocks, pair of target tiles)
     int qb2blocks, pairs_per_qb2;
+    int fuse_l1;                    // CTA-pair kernel: level 1 is pooled in the epilogue (no level-1 tiles)
     long long total_pairs;
 };
 
@@ -245,7 +247,7 @@ __device__ __forceinline__ PairCoord decode_pair(long long t, int rank, const Tc
     return c;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, float* __restrict__ pyr) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -266,7 +268,7 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 16); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -342,10 +344,18 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             if (acc == 0) accphase ^= 1;
         }
     } else if (warp >= 4) {
-        // ===================================================================== epilogue (8 warps, both CTAs)
-        const int ew = warp & 3, half = (warp - 4) >> 2;       // TMEM lanes [32*ew,+32), query columns [128*half,+128)
+        // ===================================================================== epilogue (16 warps, both CTAs)
+        // warp = (TMEM lane quarter ew, query-column quarter cq).  Level 0 is stored straight from the accumulator
+        // (lane == target: every store instruction writes two 64-byte runs).  Level 1 = 2x2 floor pooling of level 0
+        // (F.avg_pool2d, corr.py:25-27) is derived here instead of spending level-1 GEMM tiles (-21 % tensor work):
+        // a warp's 32 lanes are two 16-pixel patch rows, so the 2x2 blocks live on lane bits 0 (x) and 4 (y).  Four
+        // columns (queries) are reduced together by a transpose-reduce — 3 shuffles per 4 columns — after which the
+        // four lanes of a block hold the sums of four different queries: one store writes 4 queries x 8 cells.
+        const int ew = warp & 3, cq = (warp - 4) >> 2;         // TMEM lanes [32*ew,+32), query columns [64*cq,+64)
         const int p = ew * 32 + lane;
         const int yl = p / TC_PW, xl = p % TC_PW;
+        const bool bx = (lane & 1) != 0, by = (lane & 16) != 0;
+        const int sub = (bx ? 2 : 0) + (by ? 1 : 0);           // which of the 4 columns this lane ends up holding
         uint32_t acc = 0, accphase = 0;
         for (long long t = t_begin; t < t_end; ++t) {
             const PairCoord c = decode_pair(t, rank, P);
@@ -353,34 +363,48 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             const int y = c.ty * TC_PH + yl, x = c.tx * TC_PW + xl;
             const bool ok = c.valid && (y < Hl) && (x < Wl);
             const long long qstride = (long long)Hl * Wl;
-            const int q0 = c.qb2 * 256 + half * 128;
+            const int q0 = c.qb2 * 256 + cq * 64;
             float* out = pyr + P.lvl_off[c.level] + ((long long)c.b * P.N + q0) * qstride + (long long)y * Wl + x;
             const int nq = P.N - q0;                                // valid queries from q0 on (may be <= 0)
+            const bool pool1 = P.fuse_l1 && c.valid && c.level == 0;        // warp-uniform
+            const int y1 = c.ty * (TC_PH / 2) + ew, x1 = c.tx * (TC_PW / 2) + (xl >> 1);
+            const bool ok1 = pool1 && y1 < P.lh[1] && x1 < P.lw[1];
+            const long long q1stride = (long long)P.lh[1] * P.lw[1];
+            float* out1 = pyr + P.lvl_off[1] + ((long long)c.b * P.N + q0 + sub) * q1stride + (long long)y1 * P.lw[1] + x1;
             mbar_wait(bar_tfull + 8 * acc, accphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256 + half * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256 + cq * 64;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 64) {
-                uint32_t v0[32], v1[32];
-                tc_ld32(taddr + c0, v0);
-                tc_ld32(taddr + c0 + 32, v1);
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr + c0, v);
                 tc_wait_ld();
-                if (c0 == 64) {                                     // accumulator fully in registers: release it
+                if (c0 == 32) {                                     // this warp's accumulator slice is in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta0(bar_tempty + 8 * acc);
                 }
                 if (ok) {
-                    if (nq >= c0 + 64) {
+                    if (nq >= c0 + 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v0[j])); out += qstride; }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                        for (int j = 0; j < 32; ++j) { __stcs(out, __uint_as_float(v[j])); out += qstride; }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { if (c0 + j < nq) __stcs(out, __uint_as_float(v0[j])); out += qstride; }
+                        for (int j = 0; j < 32; ++j) { if (c0 + j < nq) __stcs(out, __uint_as_float(v[j])); out += qstride; }
+                    }
+                }
+                __syncwarp();
+                if (pool1) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { if (c0 + 32 + j < nq) __stcs(out, __uint_as_float(v1[j])); out += qstride; }
+                    for (int j = 0; j < 32; j += 4) {
+                        const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+                        const float a2 = __uint_as_float(v[j + 2]), a3 = __uint_as_float(v[j + 3]);
+                        // x pairs: lanes with bx keep columns 2,3 and hand over 0,1 (and vice versa)
+                        const float r0 = (bx ? a2 : a0) + __shfl_xor_sync(0xffffffffu, bx ? a0 : a2, 1);
+                        const float r1 = (bx ? a3 : a1) + __shfl_xor_sync(0xffffffffu, bx ? a1 : a3, 1);
+                        // y pairs: lanes with by keep the second column of their pair
+                        const float r = (by ? r1 : r0) + __shfl_xor_sync(0xffffffffu, by ? r0 : r1, 16);
+                        if (ok1 && c0 + j + sub < nq) __stcs(out1 + (long long)(c0 + j) * q1stride, 0.25f * r);
                     }
                 }
             }
@@ -407,7 +431,7 @@ struct TcPrepArgs {
     __nv_bfloat16* dst[TC_MAX_LEVELS];     // hi plane base per level; mid plane at + plane[l]
     long long plane[TC_MAX_LEVELS];        // B * H_l * W_l * C
     int h[TC_MAX_LEVELS], w[TC_MAX_LEVELS];
-    int levels, B, C;
+    int levels, B, C, skip_l1;
     const float* qsrc;                     // fmap1: blockIdx.z >= B*C/32 handles the query operand (level 0 only)
     __nv_bfloat16* qdst; long long qplane; float qscale;
 };
@@ -482,7 +506,7 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
     }
     __syncthreads();
     prep_targets_drain<0>(t0, PT_S0, 33, a.dst[0], a.plane[0], a.h[0], a.w[0], a.C, b, c0, y0, x0);
-    if (a.levels > 1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0);
+    if (a.levels > 1 && !a.skip_l1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0);
     if (a.levels > 2) prep_targets_drain<2>(t2, PT_S2, 9, a.dst[2], a.plane[2], a.h[2], a.w[2], a.C, b, c0, y0, x0);
     if (a.levels > 3) prep_targets_drain<3>(t3, PT_S3, 5, a.dst[3], a.plane[3], a.h[3], a.w[3], a.C, b, c0, y0, x0);
 }
@@ -559,9 +583,11 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     const PyramidLayout L = make_pyramid_layout(B, H, W, levels);
 
     // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
+    static const int env_fuse = [] { const char* e = getenv("PCFA_FWD_FUSE_L1"); return e ? atoi(e) : 1; }();
+    const int fuse_l1 = (two_cta && levels >= 2 && env_fuse) ? 1 : 0;
     {
         TcPrepArgs pa{};
-        pa.levels = levels; pa.B = B; pa.C = C;
+        pa.levels = levels; pa.B = B; pa.C = C; pa.skip_l1 = fuse_l1;
         pa.qsrc = fmap1; pa.qdst = reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split);
         pa.qplane = (long long)B * N * C; pa.qscale = 1.0f / sqrtf((float)C);
         for (int l = 0; l < levels; ++l) {
@@ -589,12 +615,13 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     TcParams P{};
     P.B = B; P.N = N; P.levels = levels; P.kchunks = C / TC_BK; P.qblocks = ceil_div(N, TC_BN);
     P.scale = 1.0f / sqrtf((float)C);
+    P.fuse_l1 = fuse_l1;
     int toff = 0;
     for (int l = 0; l < levels; ++l) {
         P.lh[l] = L.h[l]; P.lw[l] = L.w[l]; P.lvl_off[l] = L.off[l];
         P.tiles_x[l] = ceil_div(L.w[l], TC_PW);
         P.tile_off[l] = toff;
-        toff += P.tiles_x[l] * ceil_div(L.h[l], TC_PH);
+        if (!(fuse_l1 && l == 1)) toff += P.tiles_x[l] * ceil_div(L.h[l], TC_PH);
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)L.w[l], (cuuint64_t)L.h[l], (cuuint64_t)(2 * B)};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)L.w[l] * C * 2, (cuuint64_t)L.h[l] * L.w[l] * C * 2};
         cuuint32_t box[4] = {TC_BK, TC_PW, TC_PH, 1}, es[4] = {1, 1, 1, 1};
@@ -622,7 +649,7 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
         long long clusters = tc_num_sms() / 2;
         if (clusters > P.total_pairs) clusters = P.total_pairs;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(TC_THREADS);
+        cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(TC2_THREADS);
         cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

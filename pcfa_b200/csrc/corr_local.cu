@@ -54,13 +54,14 @@ __global__ void local_corr_fwd_generic(const float* __restrict__ in1, const floa
 }
 
 // ------------------------------------------------------------------ k=1 forward, patch row in regs
-// grid: (ceil(oW/32), oH, B*patchH) ; block: 32 x 4 (x, channel slice) ; partial sums over the 4
-// channel slices are combined through shared memory.
-template <int PW>
-__global__ void __launch_bounds__(128)
+// grid: (ceil(oW/32), oH, B*patchH) ; block: 32 x CS (x, channel slice) ; partial sums over the CS
+// channel slices are combined through shared memory.  This kernel serves the small maps (the tiled kernel takes the
+// large ones), where the serial channel loop is the critical path: hence many slices.
+template <int PW, int CS>
+__global__ void __launch_bounds__(32 * CS)
 local_corr_fwd_k1(const float* __restrict__ in1, const float* __restrict__ in2,
                   float* __restrict__ out, LocalCorrGeom g) {
-    __shared__ float red[4][PW][33];
+    __shared__ float red[CS][PW][33];
     const int w = blockIdx.x * 32 + threadIdx.x;
     const int h = blockIdx.y;
     const int n = blockIdx.z / g.patchH, ph = blockIdx.z % g.patchH;
@@ -75,7 +76,7 @@ local_corr_fwd_k1(const float* __restrict__ in1, const float* __restrict__ in2,
         const int64_t plane = (int64_t)g.iH * g.iW;
         const float* a = in1 + (int64_t)n * g.C * plane + (int64_t)i1 * g.iW + j1;
         const float* b = in2 + (int64_t)n * g.C * plane + (int64_t)i2 * g.iW;
-        for (int c = cs; c < g.C; c += 4) {
+        for (int c = cs; c < g.C; c += CS) {
             const float av = __ldg(a + c * plane);
             const float* br = b + c * plane;
 #pragma unroll
@@ -89,9 +90,10 @@ local_corr_fwd_k1(const float* __restrict__ in1, const float* __restrict__ in2,
     for (int p = 0; p < PW; ++p) red[cs][p][threadIdx.x] = acc[p];
     __syncthreads();
     if (w < g.oW) {
-        for (int p = cs; p < g.patchW; p += 4) {
-            const float v = (red[0][p][threadIdx.x] + red[1][p][threadIdx.x]) +
-                            (red[2][p][threadIdx.x] + red[3][p][threadIdx.x]);
+        for (int p = cs; p < g.patchW; p += CS) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) v += red[k][p][threadIdx.x];
             out[((((int64_t)n * g.patchH + ph) * g.patchW + p) * g.oH + h) * g.oW + w] = v * g.scale;
         }
     }
@@ -536,9 +538,9 @@ static int local_forward(const float* in1, const float* in2, float* out, const L
     if (tiled_ok(g, 9, 1) && (int64_t)g.oH * g.oW >= 4096) return launch_lc_fwd<9, 1, 3, 4, 16>(in1, in2, out, g, s);   // PWCNet
     if (tiled_ok(g, 21, 2) && (int64_t)g.oH * g.oW >= 2048) return launch_lc_fwd<21, 2, 3, 4, 16>(in1, in2, out, g, s); // FlowNet2
     if (g.kH == 1 && g.kW == 1 && g.patchW <= 21) {
-        dim3 grid(ceil_div(g.oW, 32), g.oH, g.B * g.patchH), block(32, 4);
-        if (g.patchW <= 9) local_corr_fwd_k1<9><<<grid, block, 0, s>>>(in1, in2, out, g);
-        else               local_corr_fwd_k1<21><<<grid, block, 0, s>>>(in1, in2, out, g);
+        dim3 grid(ceil_div(g.oW, 32), g.oH, g.B * g.patchH);
+        if (g.patchW <= 9) local_corr_fwd_k1<9, 16><<<grid, dim3(32, 16), 0, s>>>(in1, in2, out, g);
+        else               local_corr_fwd_k1<21, 8><<<grid, dim3(32, 8), 0, s>>>(in1, in2, out, g);
         return after_launch();
     }
     const int64_t total = (int64_t)g.B * g.patchH * g.patchW * g.oH * g.oW;

@@ -191,16 +191,19 @@ loss_partial_kernel(const float* __restrict__ flow, const float* __restrict__ ta
                     float* __restrict__ gflow, float* __restrict__ ws, int loss_type, int B, int H,
                     int W, int Hp, int Wp, int pt, int pl) {
     __shared__ float sh[LOSS_THREADS / 32];
-    const int64_t npix = (int64_t)B * Hp * Wp, ppl = (int64_t)Hp * Wp, upl = (int64_t)H * W;
+    const int64_t ppl = (int64_t)Hp * Wp, upl = (int64_t)H * W;
     const float inv_n_aee = 1.0f / (float)((int64_t)B * H * W);
     const float inv_n_mse = 1.0f / (float)((int64_t)B * 2 * H * W);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; p < npix;
-         p += (int64_t)gridDim.x * LOSS_THREADS) {
-        const int xp = (int)(p % Wp);
-        const int yp = (int)((p / Wp) % Hp);
-        const int b = (int)(p / ppl);
-        const int x = xp - pl, y = yp - pt;
+    // block k owns the padded rows [k*R/G, (k+1)*R/G): a fixed partition (deterministic partial sums) without any
+    // per-pixel 64-bit division
+    const int64_t rows = (int64_t)B * Hp;
+    const int64_t r_lo = rows * blockIdx.x / gridDim.x, r_hi = rows * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t row = r_lo; row < r_hi; ++row) {
+      const int b = (int)(row / Hp), yp = (int)(row - (int64_t)b * Hp);
+      const int y = yp - pt;
+      for (int xp = threadIdx.x; xp < Wp; xp += LOSS_THREADS) {
+        const int x = xp - pl;
         float gu = 0.f, gv = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) {
             const float fu = flow[((int64_t)b * 2 + 0) * ppl + (int64_t)yp * Wp + xp];
@@ -226,6 +229,7 @@ loss_partial_kernel(const float* __restrict__ flow, const float* __restrict__ ta
             gflow[((int64_t)b * 2 + 0) * ppl + (int64_t)yp * Wp + xp] = gu;
             gflow[((int64_t)b * 2 + 1) * ppl + (int64_t)yp * Wp + xp] = gv;
         }
+      }
     }
     const float r0 = block_sum(s0, sh);
     const float r1 = block_sum(s1, sh);
@@ -286,17 +290,17 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 loss_cosim_grad_kernel(const float* __restrict__ flow, const float* __restrict__ target,
                        const float* __restrict__ cos_sums, float* __restrict__ gflow, int B, int H,
                        int W, int Hp, int Wp, int pt, int pl) {
-    const int64_t npix = (int64_t)B * Hp * Wp, ppl = (int64_t)Hp * Wp, upl = (int64_t)H * W;
+    const int64_t ppl = (int64_t)Hp * Wp, upl = (int64_t)H * W;
     const float A = cos_sums[0], P = cos_sums[1], T = cos_sums[2];
     const float sqT = sqrtf(T), sqP = sqrtf(P);
     // d/dp [1 - A/sqrt(P)*sqrt(T)] = -sqrt(T) * ( t/sqrt(P) - A*p/P^{3/2} )
     const float c_t = -sqT / sqP, c_p = sqT * A / (P * sqP);
-    for (int64_t p = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; p < npix;
-         p += (int64_t)gridDim.x * LOSS_THREADS) {
-        const int xp = (int)(p % Wp);
-        const int yp = (int)((p / Wp) % Hp);
-        const int b = (int)(p / ppl);
-        const int x = xp - pl, y = yp - pt;
+    const int64_t rows = (int64_t)B * Hp;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int b = (int)(row / Hp), yp = (int)(row - (int64_t)b * Hp);
+      const int y = yp - pt;
+      for (int xp = threadIdx.x; xp < Wp; xp += LOSS_THREADS) {
+        const int x = xp - pl;
         float gu = 0.f, gv = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) {
             const float fu = flow[((int64_t)b * 2 + 0) * ppl + (int64_t)yp * Wp + xp];
@@ -308,6 +312,7 @@ loss_cosim_grad_kernel(const float* __restrict__ flow, const float* __restrict__
         }
         gflow[((int64_t)b * 2 + 0) * ppl + (int64_t)yp * Wp + xp] = gu;
         gflow[((int64_t)b * 2 + 1) * ppl + (int64_t)yp * Wp + xp] = gv;
+      }
     }
 }
 

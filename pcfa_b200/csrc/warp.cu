@@ -131,6 +131,8 @@ __device__ __forceinline__ WarpTaps pwc_taps(int x, int y, float fx, float fy, i
     return t;
 }
 
+// block = (pixels, channel slices): threadIdx.y walks channels c = y, y + blockDim.y, ...  Small pyramid levels (PWCNet's
+// 6x20 .. 24x80 maps with 96-196 channels) have too few pixels to fill the GPU with one thread per pixel.
 __global__ void pwc_warp_fwd_kernel(const float* __restrict__ xin, const float* __restrict__ flow,
                                     float* __restrict__ out, int B, int C, int H, int W) {
     const int64_t npix = (int64_t)B * H * W, pl = (int64_t)H * W;
@@ -150,7 +152,7 @@ __global__ void pwc_warp_fwd_kernel(const float* __restrict__ xin, const float* 
         const int ya = clampi(t.y0, 0, H - 1), yb = clampi(t.y0 + 1, 0, H - 1);
         const float* ib = xin + (int64_t)b * C * pl;
         float* ob = out + (int64_t)b * C * pl + (int64_t)y * W + x;
-        for (int c = 0; c < C; ++c) {
+        for (int c = threadIdx.y; c < C; c += blockDim.y) {
             const float* ic = ib + c * pl;
             float v = w00 * __ldg(ic + (int64_t)ya * W + xa);
             v += w01 * __ldg(ic + (int64_t)ya * W + xb);
@@ -164,12 +166,18 @@ __global__ void pwc_warp_fwd_kernel(const float* __restrict__ xin, const float* 
 __global__ void pwc_warp_bwd_kernel(const float* __restrict__ xin, const float* __restrict__ flow,
                                     const float* __restrict__ gout, float* __restrict__ gx,
                                     float* __restrict__ gflow, int B, int C, int H, int W) {
+    extern __shared__ float red[];                    // [2][blockDim.y][blockDim.x] flow-gradient partials (blockDim.y > 1)
     const int64_t npix = (int64_t)B * H * W, pl = (int64_t)H * W;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        const int x = (int)(p % W);
-        const int y = (int)((p / W) % H);
-        const int b = (int)(p / pl);
+    // every thread of a block runs the same number of iterations (the reduction below has block barriers)
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < npix; p0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p0 + threadIdx.x;
+        const bool live = p < npix;
+        float gix = 0.f, giy = 0.f;
+        int x = 0, y = 0, b = 0;
+        if (live) {
+        x = (int)(p % W);
+        y = (int)((p / W) % H);
+        b = (int)(p / pl);
         const float fx = flow[((int64_t)b * 2 + 0) * pl + (int64_t)y * W + x];
         const float fy = flow[((int64_t)b * 2 + 1) * pl + (int64_t)y * W + x];
         const WarpTaps t = pwc_taps(x, y, fx, fy, H, W);
@@ -181,9 +189,8 @@ __global__ void pwc_warp_bwd_kernel(const float* __restrict__ xin, const float* 
         const float* ib = xin + (int64_t)b * C * pl;
         float* gb = gx + (int64_t)b * C * pl;
         const float* go = gout + (int64_t)b * C * pl + (int64_t)y * W + x;
-        float gix = 0.f, giy = 0.f;
         if (t.mask != 0.f) {
-            for (int c = 0; c < C; ++c) {
+            for (int c = threadIdx.y; c < C; c += blockDim.y) {
                 const float g = __ldg(go + c * pl);
                 const float* ic = ib + c * pl;
                 float* gc = gb + c * pl;
@@ -199,9 +206,22 @@ __global__ void pwc_warp_bwd_kernel(const float* __restrict__ xin, const float* 
                 giy += g * (ax * (cq - a) + t.wx1 * (d - bq));
             }
         }
+        }
+        if (blockDim.y > 1) {                                           // ordered sum over the channel slices
+            float* rx = red + threadIdx.y * blockDim.x + threadIdx.x;
+            float* ry = rx + blockDim.y * blockDim.x;
+            *rx = gix; *ry = giy;
+            __syncthreads();
+            if (threadIdx.y == 0) {
+                for (int k = 1; k < (int)blockDim.y; ++k) { gix += rx[k * blockDim.x]; giy += ry[k * blockDim.x]; }
+            }
+            __syncthreads();
+        }
         // d ix / d flow_x = (2/max(W-1,1)) * (W/2)
-        gflow[((int64_t)b * 2 + 0) * pl + (int64_t)y * W + x] = gix * ((float)W / (float)max(W - 1, 1));
-        gflow[((int64_t)b * 2 + 1) * pl + (int64_t)y * W + x] = giy * ((float)H / (float)max(H - 1, 1));
+        if (live && threadIdx.y == 0) {
+            gflow[((int64_t)b * 2 + 0) * pl + (int64_t)y * W + x] = gix * ((float)W / (float)max(W - 1, 1));
+            gflow[((int64_t)b * 2 + 1) * pl + (int64_t)y * W + x] = giy * ((float)H / (float)max(H - 1, 1));
+        }
     }
 }
 
@@ -245,8 +265,9 @@ extern "C" int pcfa_resample2d_backward(const float* img, const float* flow, con
 extern "C" int pcfa_pwc_warp_forward(const float* x, const float* flow, float* out, int B, int C,
                                      int H, int W, pcfa_stream_t stream) {
     if (!x || !flow || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PCFA_E_BADARG;
-    pwc_warp_fwd_kernel<<<grid_pix((int64_t)B * H * W, 128), 128, 0, as_stream(stream)>>>(x, flow, out,
-                                                                                          B, C, H, W);
+    const int64_t npix = (int64_t)B * H * W;
+    const dim3 block = npix >= 32768 ? dim3(128, 1) : dim3(32, 8);
+    pwc_warp_fwd_kernel<<<grid_pix(npix, block.x), block, 0, as_stream(stream)>>>(x, flow, out, B, C, H, W);
     return after_launch();
 }
 
@@ -255,7 +276,9 @@ extern "C" int pcfa_pwc_warp_backward(const float* x, const float* flow, const f
                                       pcfa_stream_t stream) {
     if (!x || !flow || !grad_out || !grad_x || !grad_flow || B <= 0 || C <= 0 || H <= 0 || W <= 0)
         return PCFA_E_BADARG;
-    pwc_warp_bwd_kernel<<<grid_pix((int64_t)B * H * W, 128), 128, 0, as_stream(stream)>>>(
+    const int64_t npix = (int64_t)B * H * W;
+    const dim3 block = npix >= 32768 ? dim3(128, 1) : dim3(32, 8);
+    pwc_warp_bwd_kernel<<<grid_pix(npix, block.x), block, 2 * block.x * block.y * sizeof(float), as_stream(stream)>>>(
         x, flow, grad_out, grad_x, grad_flow, B, C, H, W);
     return after_launch();
 }
