@@ -6,6 +6,6 @@ from pcfa_b200.attack import pcfa_attack
 from pcfa_b200.networks.weights import synthetic_pair
 net = build_network("RAFT", device="cuda", seed=0, gain=0.5)
 i1, i2 = synthetic_pair(0, 128, 160)
-for rep in range(6):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
     r = pcfa_attack(net, "RAFT", i1.cuda(), i2.cuda(), steps=3, use_graph=bool(rep % 2))
     print(rep, [(round(h["aee_adv_tgt"], 3), round(h["aee_adv_pred"], 3), round(h["l2_delta12"], 5)) for h in r.history])
