@@ -277,7 +277,7 @@ def run_b200(args):
                                "algorithmic_bytes": top["algorithmic_bytes"], "avg_us": top["avg_us"],
                                "launches_per_step": top["launches_per_step"],
                                "peak_source": peak_src,
-                               "how": "CUDA events around each launch in an eager pass of the same step (graph replay cannot be event-bracketed per kernel)"}
+                               "how": "CUDA events around each entry-point call in an eager pass of the same step, behind a device-side spin so host enqueue latency is excluded (graph replay cannot be event-bracketed per kernel)"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, samples=args.cpu_samples)
         print(json.dumps(out), flush=True)

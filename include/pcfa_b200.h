@@ -276,6 +276,19 @@ int pcfa_objective_loss(const float* flow, const float* target,
                         pcfa_stream_t stream);
 int64_t pcfa_objective_workspace_bytes(void);
 
+/* --------------------------------------------------------------------------- encoder glue
+ * Instance normalisation with optional fused ReLU on NCHW fp32 planes: y = relu((x - mean) / sqrt(var + eps)), biased
+ * variance over H*W per (b, c) — nn.InstanceNorm2d(affine=False) + nn.ReLU as RAFT's feature encoder applies them
+ * (models/raft/extractor.py:13-55,118-150; F.instance_norm -> ATen batch_norm on a [1, B*C, H, W] view).
+ * `stats` receives (mean, rstd) per plane: [B*C][2] floats, and is an input of the backward call together with the
+ * forward INPUT x (the ReLU mask is recomputed from it).  `workspace`: pcfa_instnorm_workspace_bytes().
+ * channels_last != 0: all tensors are [B][H][W][C] in memory (torch.channels_last); needs C % 4 == 0, C <= 1024. */
+int64_t pcfa_instnorm_workspace_bytes(int B, int C, int H, int W);
+int pcfa_instnorm_forward(const float* x, float* y, float* stats, void* workspace, int B, int C, int H, int W, float eps,
+                          int relu, int channels_last, pcfa_stream_t stream);
+int pcfa_instnorm_backward(const float* x, const float* grad_y, const float* stats, float* grad_x, void* workspace,
+                           int B, int C, int H, int W, int relu, int channels_last, pcfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

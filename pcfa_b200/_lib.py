@@ -56,6 +56,9 @@ SIGNATURES = {
     "pcfa_objective_loss": (c_i, [c_fp, c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i,
                                   c_i, c_i, c_i, c_i, c_d, c_f, c_f, c_fp]),
     "pcfa_objective_workspace_bytes": (c_i64, []),
+    "pcfa_instnorm_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i]),
+    "pcfa_instnorm_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_fp]),
+    "pcfa_instnorm_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
 }
 
 
@@ -97,10 +100,14 @@ class _LibProxy:
         def timed(*args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
+            # queue filler: a ~100 us device spin keeps the GPU busy while the host marshals the ctypes call and
+            # enqueues event, launches and event — otherwise the bracket of a short entry point (two 5 us launches)
+            # times the host's enqueue latency, not the kernels
+            torch.cuda._sleep(200000)
             e0.record()
             r = fn(*args)
             e1.record()
-            _profile.setdefault(name, []).append((e0, e1))
+            _profile.setdefault(name, []).append((e0, e1, args))
             return r
         return timed
 

@@ -89,7 +89,8 @@ def compute_flow(model, network, x1, x2, test_mode=True, **kwargs):
     return model(x1, x2, **kwargs)
 
 
-def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = None, ops=None, gain: float = 1.0):
+def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = None, ops=None, gain: float = 1.0,
+                  channels_last_encoders: bool = True):
     """Construct a flow network with this package's operators (or `ops`, used by the tests to inject
     the oracle), weights from `weights` (a checkpoint path) or deterministic synthetic values."""
     from .networks.weights import deterministic_state_
@@ -115,6 +116,12 @@ def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = 
     model = model.to(device).eval()
     for p in model.parameters():
         p.requires_grad = False
+    if channels_last_encoders and torch.device(device).type == "cuda":
+        for name in ("fnet", "cnet"):                       # RAFT / GMA encoders run NHWC end to end (networks/raft.py)
+            enc = getattr(model, name, None)
+            if enc is not None:
+                enc.to(memory_format=torch.channels_last)
+                enc.channels_last = True
     return model
 
 

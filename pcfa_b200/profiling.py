@@ -34,6 +34,15 @@ def algorithmic_bytes(name: str, *, B: int, C: int, H: int, W: int, levels: int 
     return None
 
 
+def call_bytes(name: str, args):
+    """Minimum HBM bytes of ONE call from its own arguments (entry points whose shape changes from call to call)."""
+    if name == "pcfa_instnorm_forward":                  # (x, y, stats, ws, B, C, H, W, ...): read x, write y
+        return 4 * 2 * args[4] * args[5] * args[6] * args[7]
+    if name == "pcfa_instnorm_backward":                 # (x, gy, stats, gx, ws, B, C, H, W, ...): read x, gy, write gx
+        return 4 * 3 * args[5] * args[6] * args[7] * args[8]
+    return None
+
+
 def kernel_table(step_fn, n_steps: int, *, B: int, C: int, H: int, W: int, iters: int, peak_gbs: float,
                  img_numel: int = 0, flow_numel: int = 0):
     """Run `step_fn` n_steps times with event bracketing and return one row per entry point."""
@@ -49,10 +58,14 @@ def kernel_table(step_fn, n_steps: int, *, B: int, C: int, H: int, W: int, iters
         _lib.set_profile(None)
     rows = []
     for name, evs in store.items():
-        us = [a.elapsed_time(b) * 1e3 for a, b in evs]
+        us = [a.elapsed_time(b) * 1e3 for a, b, _ in evs]
         per_step = len(us) / n_steps
         avg = sum(us) / len(us)
         ab = algorithmic_bytes(name, B=B, C=C, H=H, W=W, img_numel=img_numel, flow_numel=flow_numel)
+        if ab is None:                                   # shape varies per call: average the per-call minimum
+            per_call = [call_bytes(name, args) for _, _, args in evs]
+            if per_call and all(v is not None for v in per_call):
+                ab = int(sum(per_call) / len(per_call))
         row = {"name": name, "launches_per_step": per_step, "avg_us": round(avg, 2),
                "total_us_per_step": round(avg * per_step, 1), "algorithmic_bytes": ab}
         if ab:

@@ -1,0 +1,50 @@
+"""Kernel-time breakdown of one eager RAFT closure with torch.profiler (CUPTI; no serialisation, warm caches).
+usage: python scripts/profile_closure.py [nchw|cl] [topN]"""
+import sys, collections, torch
+sys.path.insert(0, '.')
+import bench
+from pcfa_b200 import _lib, objective as J
+from torch.profiler import profile, ProfilerActivity
+fmt = sys.argv[1] if len(sys.argv) > 1 else "nchw"
+topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+_lib.load()
+device = torch.device("cuda", 0)
+torch.backends.cudnn.benchmark = True
+net, i1, i2 = bench.make_problem(device, 0, 436, 1024)
+if fmt == "cl":
+    net = net.to(memory_format=torch.channels_last)
+padder, img1, img2 = bench.prepare_on_device(i1.pin_memory(), i2.pin_memory(), device)
+target = torch.zeros(1, 2, 436, 1024, device=device)
+fo = J.FusedObjective(lambda a, b: net(a, b, iters=12, test_mode=True)[1], img1, img2, target, mode=J.BOX_COV, joint=False,
+                      pad=padder.top_left, eps_box=bench.EPS_BOX, scale=255.0, delta_bound=bench.DELTA_BOUND, mu=bench.MU, loss="aee")
+w1, w2 = bench.init_vars(img1), bench.init_vars(img2)
+g1, g2 = torch.empty_like(w1), torch.empty_like(w2)
+for _ in range(4):
+    fo.evaluate(w1, w2, g1, g2)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    fo.evaluate(w1, w2, g1, g2)
+e1.record(); torch.cuda.synchronize()
+print("eager closure ms:", e0.elapsed_time(e1) / 3)
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    fo.evaluate(w1, w2, g1, g2)
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        agg[ev.name][0] += 1; agg[ev.name][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+tot = sum(v[1] for v in agg.values())
+print(f"{len(agg)} kernels, {sum(v[0] for v in agg.values())} launches, {tot:.0f} us of kernel time")
+groups = collections.OrderedDict([("layout conversions", ("nchwToNhwc", "nhwcToNchw", "tensorTransform", "transpose")), ("norms", ("batch_norm", "bn_fw", "bn_bw")),
+          ("convs/gemms", ("cutlass", "xmma", "implicit_convolve", "dgrad", "wgrad", "winograd", "sgemm", "gemm", "conv")), ("pcfa", ("pcfa::",)),
+          ("elementwise/cat/other", ("",))])
+gs = collections.OrderedDict((k, 0.0) for k in groups)
+for name, (n, t) in agg.items():
+    for gname, keys in groups.items():
+        if any(k in name for k in keys):
+            gs[gname] += t; break
+print({k: round(v) for k, v in gs.items()})
+for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
+    print(f"{t:9.0f} us {n:5d}  {name[:110]}")

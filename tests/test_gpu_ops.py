@@ -376,3 +376,30 @@ def test_allpairs_backward_tcgen05_matches_fp32_simt(shape, levels, impl):
         rel = float((a - b).norm() / b.norm())
         mx = float((a - b).abs().max() / b.pow(2).mean().sqrt())
         assert rel < 1e-3 and mx < 6e-3, f"{name}: rel L2 {rel:.2e}, max/rms {mx:.2e}"
+
+
+# ----------------------------------------------------------------------------------- encoder glue (f-4)
+@pytest.mark.parametrize("shape", [(2, 8, 37, 53), (1, 16, 32, 64), (1, 4, 220, 512), (3, 5, 1, 7), (2, 96, 20, 24)])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_instance_norm_matches_torch(shape, relu, channels_last):
+    """Fused instance norm (+ReLU) vs F.instance_norm (+F.relu) on the same GPU: values and input gradient.
+    (models/raft/extractor.py:13-55: nn.InstanceNorm2d(affine=False), eps 1e-5, biased variance.)"""
+    import torch.nn.functional as F
+    from pcfa_b200.instance_norm import instance_norm
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g) * 3 + 1.5).cuda()
+    go = torch.randn(shape, generator=g).cuda()
+    if channels_last:                                   # [B][H][W][C] memory; C % 4 != 0 falls back to the NCHW kernels
+        x = x.contiguous(memory_format=torch.channels_last)
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = instance_norm(xa, eps=1e-5, relu=relu)
+    if channels_last and shape[1] % 4 == 0 and shape[1] > 1:
+        assert ya.is_contiguous(memory_format=torch.channels_last)
+    yb = F.instance_norm(xb, eps=1e-5)
+    yb = F.relu(yb) if relu else yb
+    assert_close(npy(ya), npy(yb), what="instance norm", rtol=1e-5, atol_rms=1e-5)
+    (ya * go).sum().backward()
+    (yb * go).sum().backward()
+    assert_close(npy(xa.grad), npy(xb.grad), what="instance norm grad", rtol=1e-4, atol_rms=1e-4)
