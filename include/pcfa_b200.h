@@ -289,6 +289,17 @@ int pcfa_instnorm_forward(const float* x, float* y, float* stats, void* workspac
 int pcfa_instnorm_backward(const float* x, const float* grad_y, const float* stats, float* grad_x, void* workspace,
                            int B, int C, int H, int W, int relu, int channels_last, pcfa_stream_t stream);
 
+/* Element-wise halves of the convolutional GRU (models/raft/update.py:16-60): z = sigmoid, r = sigmoid, rh = r*h from the
+ * concatenated pre-activations zr = [B][2C][H*W] (z first; n = C*H*W elements per sample), and the state update
+ * q = tanh(q_pre), h_new = (1-z)*h + z*q.  All tensors NCHW-contiguous fp32.  grad_z / grad_rh may be NULL (= zero). */
+int pcfa_gru_gates_forward(const float* zr, const float* h, float* z, float* r, float* rh, int B, int64_t n, pcfa_stream_t stream);
+int pcfa_gru_gates_backward(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rh,
+                            float* grad_zr, float* grad_h, int B, int64_t n, pcfa_stream_t stream);
+int pcfa_gru_blend_forward(const float* z, const float* q_pre, const float* h, float* q, float* h_new, int64_t numel,
+                           pcfa_stream_t stream);
+int pcfa_gru_blend_backward(const float* z, const float* q, const float* h, const float* grad_h_new, float* grad_z,
+                            float* grad_q_pre, float* grad_h, int64_t numel, pcfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

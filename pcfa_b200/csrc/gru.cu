@@ -1,0 +1,144 @@
+// Element-wise halves of RAFT/GMA's convolutional GRU (models/raft/update.py:16-60, SepConvGRU / ConvGRU):
+//     z = sigmoid(convz(hx)); r = sigmoid(convr(hx)); q = tanh(convq([r*h, x])); h' = (1-z)*h + z*q
+// The convolutions stay in cuDNN (convz and convr share their input and run as ONE convolution with concatenated
+// output channels); the eight element-wise ATen launches per GRU step forward (and ~ten backward) become two each.
+// At 55x128 features every launch is ~4 us of latency for 3.6 MB of data, and RAFT runs 24 GRU steps per closure, so
+// the launch count, not the bytes, is what these kernels remove (row f-4 of SURVEY.md section 8).
+//   gates : zr = [B][2C][HW] pre-activations (z first), h = [B][C][HW]  ->  z, r, rh = r*h
+//   blend : z, qc (pre-activation), h                                   ->  q = tanh(qc), h' = (1-z)*h + z*q
+#include "common.cuh"
+#include <math.h>
+
+namespace pcfa {
+
+constexpr int GRU_THREADS = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename F>
+__device__ __forceinline__ void gru_for_each4(int64_t n, int vec, F f) {
+    if (vec) {
+        for (int64_t i = 4 * ((int64_t)blockIdx.x * GRU_THREADS + threadIdx.x); i < n; i += 4 * (int64_t)gridDim.x * GRU_THREADS) f(i, 4);
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * GRU_THREADS) f(i, 1);
+    }
+}
+
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_gates_fwd_kernel(const float* __restrict__ zr, const float* __restrict__ h, float* __restrict__ z, float* __restrict__ r,
+                     float* __restrict__ rh, int64_t n, int vec) {
+    const int64_t b = blockIdx.y;
+    const float* zc = zr + b * 2 * n; const float* rc = zc + n;
+    const float* hb = h + b * n; float* zb = z + b * n; float* rb = r + b * n; float* rhb = rh + b * n;
+    gru_for_each4(n, vec, [&](int64_t i, int w) {
+        if (w == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(zc + i)), c = __ldg(reinterpret_cast<const float4*>(rc + i));
+            const float4 hv = __ldg(reinterpret_cast<const float4*>(hb + i));
+            const float4 zz = make_float4(sigmoidf_(a.x), sigmoidf_(a.y), sigmoidf_(a.z), sigmoidf_(a.w));
+            const float4 rr = make_float4(sigmoidf_(c.x), sigmoidf_(c.y), sigmoidf_(c.z), sigmoidf_(c.w));
+            *reinterpret_cast<float4*>(zb + i) = zz;
+            *reinterpret_cast<float4*>(rb + i) = rr;
+            *reinterpret_cast<float4*>(rhb + i) = make_float4(rr.x * hv.x, rr.y * hv.y, rr.z * hv.z, rr.w * hv.w);
+        } else {
+            const float zz = sigmoidf_(zc[i]), rr = sigmoidf_(rc[i]);
+            zb[i] = zz; rb[i] = rr; rhb[i] = rr * hb[i];
+        }
+    });
+}
+
+// dz, drh (either may be NULL = zero)  ->  dzr = [B][2C][HW] (dz*z*(1-z) | drh*h*r*(1-r)),  dh = drh * r
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_gates_bwd_kernel(const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ h,
+                     const float* __restrict__ dz, const float* __restrict__ drh, float* __restrict__ dzr,
+                     float* __restrict__ dh, int64_t n, int vec) {
+    const int64_t b = blockIdx.y;
+    const float* zb = z + b * n; const float* rb = r + b * n; const float* hb = h + b * n;
+    const float* dzb = dz ? dz + b * n : nullptr; const float* drhb = drh ? drh + b * n : nullptr;
+    float* dzc = dzr + b * 2 * n; float* drc = dzc + n; float* dhb = dh + b * n;
+    gru_for_each4(n, vec, [&](int64_t i, int w) {
+        for (int k = 0; k < w; ++k) {
+            const float zz = zb[i + k], rr = rb[i + k], hv = hb[i + k];
+            const float gz = dzb ? dzb[i + k] : 0.f, grh = drhb ? drhb[i + k] : 0.f;
+            dzc[i + k] = gz * zz * (1.f - zz);
+            drc[i + k] = grh * hv * rr * (1.f - rr);
+            dhb[i + k] = grh * rr;
+        }
+    });
+}
+
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_blend_fwd_kernel(const float* __restrict__ z, const float* __restrict__ qc, const float* __restrict__ h,
+                     float* __restrict__ q, float* __restrict__ hn, int64_t n, int vec) {
+    gru_for_each4(n, vec, [&](int64_t i, int w) {
+        for (int k = 0; k < w; ++k) {
+            const float zz = z[i + k], qq = tanhf(qc[i + k]), hv = h[i + k];
+            q[i + k] = qq;
+            hn[i + k] = (1.f - zz) * hv + zz * qq;
+        }
+    });
+}
+
+// dhn -> dz = dhn*(q-h), dqc = dhn*z*(1-q^2), dh = dhn*(1-z)
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_blend_bwd_kernel(const float* __restrict__ z, const float* __restrict__ q, const float* __restrict__ h,
+                     const float* __restrict__ dhn, float* __restrict__ dz, float* __restrict__ dqc, float* __restrict__ dh,
+                     int64_t n, int vec) {
+    gru_for_each4(n, vec, [&](int64_t i, int w) {
+        for (int k = 0; k < w; ++k) {
+            const float zz = z[i + k], qq = q[i + k], hv = h[i + k], g = dhn[i + k];
+            dz[i + k] = g * (qq - hv);
+            dqc[i + k] = g * zz * (1.f - qq * qq);
+            dh[i + k] = g * (1.f - zz);
+        }
+    });
+}
+
+static int gru_grid(int64_t n, int vec) {
+    const int64_t per = (int64_t)GRU_THREADS * (vec ? 4 : 1);
+    int64_t b = (n + per - 1) / per;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+static int aligned16(std::initializer_list<const void*> ps) {
+    uintptr_t a = 0;
+    for (const void* p : ps) a |= reinterpret_cast<uintptr_t>(p);
+    return (a & 15) == 0;
+}
+
+}  // namespace pcfa
+
+using namespace pcfa;
+
+extern "C" int pcfa_gru_gates_forward(const float* zr, const float* h, float* z, float* r, float* rh, int B, int64_t n,
+                                      pcfa_stream_t stream) {
+    if (!zr || !h || !z || !r || !rh || B <= 0 || n <= 0 || B > 65535) return PCFA_E_BADARG;
+    const int vec = (n % 4 == 0 && aligned16({zr, h, z, r, rh})) ? 1 : 0;
+    gru_gates_fwd_kernel<<<dim3(gru_grid(n, vec), B), GRU_THREADS, 0, as_stream(stream)>>>(zr, h, z, r, rh, n, vec);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_gates_backward(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rh,
+                                       float* grad_zr, float* grad_h, int B, int64_t n, pcfa_stream_t stream) {
+    if (!z || !r || !h || !grad_zr || !grad_h || B <= 0 || n <= 0 || B > 65535) return PCFA_E_BADARG;
+    const int vec = (n % 4 == 0) ? 1 : 0;
+    gru_gates_bwd_kernel<<<dim3(gru_grid(n, vec), B), GRU_THREADS, 0, as_stream(stream)>>>(z, r, h, grad_z, grad_rh, grad_zr,
+                                                                                          grad_h, n, vec);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_blend_forward(const float* z, const float* q_pre, const float* h, float* q, float* h_new, int64_t numel,
+                                      pcfa_stream_t stream) {
+    if (!z || !q_pre || !h || !q || !h_new || numel <= 0) return PCFA_E_BADARG;
+    const int vec = (numel % 4 == 0) ? 1 : 0;
+    gru_blend_fwd_kernel<<<gru_grid(numel, vec), GRU_THREADS, 0, as_stream(stream)>>>(z, q_pre, h, q, h_new, numel, vec);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_blend_backward(const float* z, const float* q, const float* h, const float* grad_h_new, float* grad_z,
+                                       float* grad_q_pre, float* grad_h, int64_t numel, pcfa_stream_t stream) {
+    if (!z || !q || !h || !grad_h_new || !grad_z || !grad_q_pre || !grad_h || numel <= 0) return PCFA_E_BADARG;
+    const int vec = (numel % 4 == 0) ? 1 : 0;
+    gru_blend_bwd_kernel<<<gru_grid(numel, vec), GRU_THREADS, 0, as_stream(stream)>>>(z, q, h, grad_h_new, grad_z, grad_q_pre,
+                                                                                     grad_h, numel, vec);
+    return after_launch();
+}

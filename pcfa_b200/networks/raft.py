@@ -200,7 +200,28 @@ class FlowHead(nn.Module):
         return self.conv2(self.relu(self.conv1(x)))
 
 
+def _zr_weights(cz: nn.Conv2d, cr: nn.Conv2d):
+    """convz and convr read the same input: run them as one convolution with concatenated output channels (frozen
+    weights; cached, the key notices in-place updates and re-allocation)."""
+    ts = (cz.weight, cz.bias, cr.weight, cr.bias)
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    cache = getattr(cz, "_pcfa_zr", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, torch.cat([cz.weight, cr.weight], dim=0).contiguous(), torch.cat([cz.bias, cr.bias], dim=0).contiguous())
+        cz._pcfa_zr = cache
+    return cache[1], cache[2]
+
+
 def _gru_step(h, x, cz, cr, cq):
+    from .. import gru_ops
+    frozen = not any(p.requires_grad for m in (cz, cr) for p in m.parameters())
+    if gru_ops.usable(h, x) and frozen and cz.bias is not None and cr.bias is not None:
+        # GPU path: one convolution for both gates, two fused element-wise launches (pcfa_b200/csrc/gru.cu)
+        hx = torch.cat([h, x], dim=1)
+        w, b = _zr_weights(cz, cr)
+        z, rh = gru_ops.gru_gates(F.conv2d(hx, w, b, cz.stride, cz.padding), h)
+        return gru_ops.gru_blend(z, cq(torch.cat([rh, x], dim=1)), h)
     hx = torch.cat([h, x], dim=1)
     z = torch.sigmoid(cz(hx))
     r = torch.sigmoid(cr(hx))

@@ -403,3 +403,29 @@ def test_instance_norm_matches_torch(shape, relu, channels_last):
     (ya * go).sum().backward()
     (yb * go).sum().backward()
     assert_close(npy(xa.grad), npy(xb.grad), what="instance norm grad", rtol=1e-4, atol_rms=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 55, 128), (2, 96, 7, 9), (3, 5, 3, 3)])
+def test_fused_gru_elementwise_matches_torch(shape):
+    """gru_gates / gru_blend vs the reference's element-wise composition (models/raft/update.py:16-31), values and
+    every input gradient."""
+    from pcfa_b200.gru_ops import gru_blend, gru_gates
+    g = torch.Generator().manual_seed(sum(shape))
+    B, C, H, W = shape
+    zr0, h0, qp0 = torch.randn(B, 2 * C, H, W, generator=g).cuda(), torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+    go = torch.randn(shape, generator=g).cuda()
+    outs = []
+    for fused in (True, False):
+        zr, h, qp = (t.clone().requires_grad_(True) for t in (zr0, h0, qp0))
+        if fused:
+            z, rh = gru_gates(zr, h)
+            hn = gru_blend(z, qp + rh, h)                   # rh feeds q_pre like convq([r*h, x]) would
+        else:
+            z, r = torch.sigmoid(zr[:, :C]), torch.sigmoid(zr[:, C:])
+            rh = r * h
+            q = torch.tanh(qp + rh)
+            hn = (1 - z) * h + z * q
+        (hn * go).sum().backward()
+        outs.append((hn, zr.grad, h.grad, qp.grad))
+    for name, a, b in zip(("h_new", "grad zr", "grad h", "grad q_pre"), outs[0], outs[1]):
+        assert_close(npy(a), npy(b), what=name, rtol=1e-5, atol_rms=1e-6)
