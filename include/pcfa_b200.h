@@ -95,6 +95,11 @@ int pcfa_corr_lookup_forward(const float* pyramid, const float* coords,
                              int B, int H, int W, int num_levels, int radius,
                              pcfa_stream_t stream);
 
+/* channels-last variants: out / grad_out are [B][H][W][num_levels*(2r+1)^2] in memory (torch.channels_last) */
+int pcfa_corr_lookup_forward_cl(const float* pyramid, const float* coords, float* out, int B, int H, int W,
+                                int num_levels, int radius, pcfa_stream_t stream);
+int pcfa_corr_lookup_backward_cl(const float* grad_out, const float* coords, float* grad_pyramid, int B, int H, int W,
+                                 int num_levels, int radius, pcfa_stream_t stream);
 int pcfa_corr_lookup_backward(const float* grad_out, const float* coords,
                               float* grad_pyramid /* (accumulated) */,
                               int B, int H, int W, int num_levels, int radius,
@@ -292,13 +297,20 @@ int pcfa_instnorm_backward(const float* x, const float* grad_y, const float* sta
 /* Element-wise halves of the convolutional GRU (models/raft/update.py:16-60): z = sigmoid, r = sigmoid, rh = r*h from the
  * concatenated pre-activations zr = [B][2C][H*W] (z first; n = C*H*W elements per sample), and the state update
  * q = tanh(q_pre), h_new = (1-z)*h + z*q.  All tensors NCHW-contiguous fp32.  grad_z / grad_rh may be NULL (= zero). */
-int pcfa_gru_gates_forward(const float* zr, const float* h, float* z, float* r, float* rh, int B, int64_t n, pcfa_stream_t stream);
+int pcfa_gru_gates_forward(const float* zr, const float* h, float* z, float* r, float* rh, int B, int64_t n,
+                           int channels_last_C /* 0: NCHW; C: all tensors channels-last with C (2C for zr) channels */,
+                           pcfa_stream_t stream);
 int pcfa_gru_gates_backward(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rh,
-                            float* grad_zr, float* grad_h, int B, int64_t n, pcfa_stream_t stream);
+                            float* grad_zr, float* grad_h, int B, int64_t n, int channels_last_C, pcfa_stream_t stream);
 int pcfa_gru_blend_forward(const float* z, const float* q_pre, const float* h, float* q, float* h_new, int64_t numel,
                            pcfa_stream_t stream);
 int pcfa_gru_blend_backward(const float* z, const float* q, const float* h, const float* grad_h_new, float* grad_z,
                             float* grad_q_pre, float* grad_h, int64_t numel, pcfa_stream_t stream);
+
+/* Channel concatenation of up to four channels-last tensors [npix][C_k] -> [npix][sum C_k] (torch.cat(dim=1) of
+ * torch.channels_last tensors, which ATen runs on a slow path). */
+int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,
+                           pcfa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,8 @@ SIGNATURES = {
     "pcfa_corr_pyramid_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_corr_lookup_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_corr_lookup_backward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_lookup_forward_cl": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_lookup_backward_cl": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_scs_output_size": (c_i, [c_i, c_i, C.POINTER(ScsParams), C.POINTER(c_i), C.POINTER(c_i)]),
     "pcfa_scs_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),
     "pcfa_scs_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),
@@ -58,10 +60,11 @@ SIGNATURES = {
     "pcfa_objective_workspace_bytes": (c_i64, []),
     "pcfa_instnorm_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i]),
     "pcfa_instnorm_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_fp]),
-    "pcfa_gru_gates_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_fp]),
-    "pcfa_gru_gates_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_fp]),
+    "pcfa_gru_gates_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_i, c_fp]),
+    "pcfa_gru_gates_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_i, c_fp]),
     "pcfa_gru_blend_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_gru_blend_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
+    "pcfa_cat_channels_last": (c_i, [c_fp, c_fp, c_i, c_fp, c_i64, c_fp]),
     "pcfa_instnorm_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
 }
 

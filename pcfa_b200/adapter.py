@@ -90,7 +90,7 @@ def compute_flow(model, network, x1, x2, test_mode=True, **kwargs):
 
 
 def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = None, ops=None, gain: float = 1.0,
-                  channels_last_encoders: bool = True):
+                  channels_last_encoders: bool = True, channels_last_update: bool = True):
     """Construct a flow network with this package's operators (or `ops`, used by the tests to inject
     the oracle), weights from `weights` (a checkpoint path) or deterministic synthetic values."""
     from .networks.weights import deterministic_state_
@@ -122,6 +122,9 @@ def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = 
             if enc is not None:
                 enc.to(memory_format=torch.channels_last)
                 enc.channels_last = True
+        if net == "RAFT" and channels_last_update:             # NHWC update block: networks/raft.py, BasicUpdateBlock.forward
+            model.update_block.to(memory_format=torch.channels_last)
+            model.update_block.channels_last = True
     return model
 
 

@@ -89,17 +89,18 @@ class _BuildPyramid(torch.autograd.Function):
 
 class _Lookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pyr, coords, state, radius):
+    def forward(ctx, pyr, coords, state, radius, channels_last=False):
         lib = _lib.load()
         _lib.require_cuda(pyr, coords, name="CorrBlock.__call__")
         B, H, W, L = state.B, state.H, state.W, state.levels
         D = 2 * radius + 1
-        out = torch.empty((B, L * D * D, H, W), device=pyr.device, dtype=torch.float32)
-        _lib.check(lib.pcfa_corr_lookup_forward(_lib.ptr(pyr), _lib.ptr(coords), _lib.ptr(out),
-                                                B, H, W, L, radius, _lib.stream()),
+        fmt = torch.channels_last if channels_last else torch.contiguous_format
+        out = torch.empty((B, L * D * D, H, W), device=pyr.device, dtype=torch.float32, memory_format=fmt)
+        fn = lib.pcfa_corr_lookup_forward_cl if channels_last else lib.pcfa_corr_lookup_forward
+        _lib.check(fn(_lib.ptr(pyr), _lib.ptr(coords), _lib.ptr(out), B, H, W, L, radius, _lib.stream()),
                    "pcfa_corr_lookup_forward")
         ctx.save_for_backward(coords)
-        ctx.state, ctx.radius = state, radius
+        ctx.state, ctx.radius, ctx.cl = state, radius, bool(channels_last)
         return out
 
     @staticmethod
@@ -109,13 +110,13 @@ class _Lookup(torch.autograd.Function):
         st = ctx.state
         if st.grad is None:
             st.grad = torch.zeros(st.total, device=gout.device, dtype=torch.float32)
-        gout = gout.contiguous()
-        _lib.check(lib.pcfa_corr_lookup_backward(_lib.ptr(gout), _lib.ptr(coords), _lib.ptr(st.grad),
-                                                 st.B, st.H, st.W, st.levels, ctx.radius,
-                                                 _lib.stream()), "pcfa_corr_lookup_backward")
+        gout = gout.contiguous(memory_format=torch.channels_last) if ctx.cl else gout.contiguous()
+        fn = lib.pcfa_corr_lookup_backward_cl if ctx.cl else lib.pcfa_corr_lookup_backward
+        _lib.check(fn(_lib.ptr(gout), _lib.ptr(coords), _lib.ptr(st.grad), st.B, st.H, st.W, st.levels, ctx.radius,
+                      _lib.stream()), "pcfa_corr_lookup_backward")
         # the pyramid's gradient travels through st.grad (consumed by _BuildPyramid.backward, which
         # autograd runs after every lookup node); coords are detached in RAFT/GMA (raft.py:123)
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class CorrBlock:
@@ -132,9 +133,11 @@ class CorrBlock:
         self.corr_pyramid = [self._flat[offs[l]:offs[l + 1]].view(N, 1, hs[l], ws[l])
                              for l in range(num_levels)]
 
-    def __call__(self, coords):
+    def __call__(self, coords, channels_last=False):
+        """[B, levels*(2r+1)^2, H, W]; channels_last=True returns the same values in torch.channels_last memory
+        (what an NHWC update block consumes without a layout conversion)."""
         coords = coords.detach().float().contiguous()
-        return _Lookup.apply(self._flat, coords, self._state, self.radius)
+        return _Lookup.apply(self._flat, coords, self._state, self.radius, channels_last)
 
     @staticmethod
     def corr(fmap1, fmap2):

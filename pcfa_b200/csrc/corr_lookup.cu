@@ -40,7 +40,7 @@ __device__ __forceinline__ LookupGeom lookup_geom(float cx, float cy, int level,
 template <int RT>
 __global__ void __launch_bounds__(LOOKUP_THREADS)
 corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restrict__ coords,
-                       float* __restrict__ out, PyramidLayout L, int B, int H, int W, int r_rt) {
+                       float* __restrict__ out, PyramidLayout L, int B, int H, int W, int r_rt, int out_cl) {
     extern __shared__ float smem[];
     const int r = RT > 0 ? RT : r_rt;
     const int D = 2 * r + 1, F = D + 1, FP = F * F;
@@ -95,6 +95,23 @@ corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restric
     }
     __syncthreads();
 
+    if (out_cl) {
+        // channels-last output [B][N][levels*D*D]: warp = query, lanes = channels -> 324-byte contiguous runs
+        const int nch = D * D, CT = L.levels * nch;
+        for (int qi = warp; qi < nq; qi += LOOKUP_THREADS / 32) {
+            const LookupGeom g = geom[qi];
+            const float w00 = (1.f - g.fx) * (1.f - g.fy), w01 = g.fx * (1.f - g.fy);
+            const float w10 = (1.f - g.fx) * g.fy,         w11 = g.fx * g.fy;
+            const float* Sq = S + qi * FS;
+            float* o = out + ((int64_t)b * N + q0 + qi) * CT + (int64_t)l * nch;
+            for (int ch = lane; ch < nch; ch += 32) {
+                const int a = ch / D, bb = ch - a * D;
+                const float* p = Sq + bb * F + a;
+                o[ch] = w00 * p[0] + w01 * p[1] + w10 * p[F] + w11 * p[F + 1];
+            }
+        }
+        return;
+    }
     if (lane < nq) {
         const LookupGeom g = geom[lane];
         const float w00 = (1.f - g.fx) * (1.f - g.fy), w01 = g.fx * (1.f - g.fy);
@@ -117,7 +134,7 @@ corr_lookup_fwd_kernel(const float* __restrict__ pyramid, const float* __restric
 template <int RT>
 __global__ void __launch_bounds__(LOOKUP_THREADS)
 corr_lookup_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ coords,
-                       float* __restrict__ gpyr, PyramidLayout L, int B, int H, int W, int r_rt) {
+                       float* __restrict__ gpyr, PyramidLayout L, int B, int H, int W, int r_rt, int out_cl) {
     extern __shared__ float smem[];
     const int r = RT > 0 ? RT : r_rt;
     const int D = 2 * r + 1, F = D + 1, FP = F * F, nch = D * D;
@@ -140,7 +157,13 @@ corr_lookup_bwd_kernel(const float* __restrict__ gout, const float* __restrict__
         const float cy = coords[((int64_t)b * 2 + 1) * N + q];
         geom[threadIdx.x] = lookup_geom(cx, cy, l, r);
     }
-    if (lane < nq) {
+    if (out_cl) {                                  // grad_out is [B][N][levels*D*D]: warp = query, lanes = channels
+        const int CT = L.levels * nch;
+        for (int qi = warp; qi < nq; qi += LOOKUP_THREADS / 32) {
+            const float* gi = gout + ((int64_t)b * N + q0 + qi) * CT + (int64_t)l * nch;
+            for (int ch = lane; ch < nch; ch += 32) G[qi * GS + ch] = __ldg(gi + ch);
+        }
+    } else if (lane < nq) {
         const float* gi = gout + ((int64_t)b * (L.levels * nch) + (int64_t)l * nch) * N + q0 + lane;
         for (int ch = warp; ch < nch; ch += LOOKUP_THREADS / 32)
             G[lane * GS + ch] = __ldg(gi + (int64_t)ch * N);
@@ -185,40 +208,56 @@ static int lookup_check(const void* a, const void* b, const void* c, int B, int 
     return PCFA_OK;
 }
 
-extern "C" int pcfa_corr_lookup_forward(const float* pyramid, const float* coords, float* out, int B,
-                                        int H, int W, int num_levels, int radius,
-                                        pcfa_stream_t stream) {
+static int lookup_forward(const float* pyramid, const float* coords, float* out, int B, int H, int W, int num_levels,
+                          int radius, int out_cl, pcfa_stream_t stream) {
     PCFA_TRY(lookup_check(pyramid, coords, out, B, H, W, num_levels, radius));
     const PyramidLayout L = make_pyramid_layout(B, H, W, num_levels);
     const int D = 2 * radius + 1, FP = (D + 1) * (D + 1);
     const size_t smem = (size_t)QB * (FP | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);
     cudaStream_t s = as_stream(stream);
-    if (radius == 4)      corr_lookup_fwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
-    else if (radius == 3) corr_lookup_fwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
+    if (radius == 4)      corr_lookup_fwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius, out_cl);
+    else if (radius == 3) corr_lookup_fwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius, out_cl);
     else {
         if (smem > 48 * 1024)
             PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        corr_lookup_fwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius);
+        corr_lookup_fwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(pyramid, coords, out, L, B, H, W, radius, out_cl);
     }
     return after_launch();
 }
 
-extern "C" int pcfa_corr_lookup_backward(const float* grad_out, const float* coords,
-                                         float* grad_pyramid, int B, int H, int W, int num_levels,
-                                         int radius, pcfa_stream_t stream) {
+static int lookup_backward(const float* grad_out, const float* coords, float* grad_pyramid, int B, int H, int W,
+                           int num_levels, int radius, int out_cl, pcfa_stream_t stream) {
     PCFA_TRY(lookup_check(grad_out, coords, grad_pyramid, B, H, W, num_levels, radius));
     const PyramidLayout L = make_pyramid_layout(B, H, W, num_levels);
     const int D = 2 * radius + 1;
     const size_t smem = (size_t)QB * ((D * D) | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);
     cudaStream_t s = as_stream(stream);
-    if (radius == 4)      corr_lookup_bwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
-    else if (radius == 3) corr_lookup_bwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
+    if (radius == 4)      corr_lookup_bwd_kernel<4><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius, out_cl);
+    else if (radius == 3) corr_lookup_bwd_kernel<3><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius, out_cl);
     else {
         if (smem > 48 * 1024)
             PCFA_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        corr_lookup_bwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius);
+        corr_lookup_bwd_kernel<0><<<grid, LOOKUP_THREADS, smem, s>>>(grad_out, coords, grad_pyramid, L, B, H, W, radius, out_cl);
     }
     return after_launch();
+}
+
+extern "C" int pcfa_corr_lookup_forward(const float* pyramid, const float* coords, float* out, int B, int H, int W,
+                                        int num_levels, int radius, pcfa_stream_t stream) {
+    return lookup_forward(pyramid, coords, out, B, H, W, num_levels, radius, 0, stream);
+}
+extern "C" int pcfa_corr_lookup_backward(const float* grad_out, const float* coords, float* grad_pyramid, int B, int H,
+                                         int W, int num_levels, int radius, pcfa_stream_t stream) {
+    return lookup_backward(grad_out, coords, grad_pyramid, B, H, W, num_levels, radius, 0, stream);
+}
+// channels-last variants: out / grad_out are [B][H][W][levels*(2r+1)^2] in memory (torch.channels_last of [B,C,H,W])
+extern "C" int pcfa_corr_lookup_forward_cl(const float* pyramid, const float* coords, float* out, int B, int H, int W,
+                                           int num_levels, int radius, pcfa_stream_t stream) {
+    return lookup_forward(pyramid, coords, out, B, H, W, num_levels, radius, 1, stream);
+}
+extern "C" int pcfa_corr_lookup_backward_cl(const float* grad_out, const float* coords, float* grad_pyramid, int B, int H,
+                                            int W, int num_levels, int radius, pcfa_stream_t stream) {
+    return lookup_backward(grad_out, coords, grad_pyramid, B, H, W, num_levels, radius, 1, stream);
 }

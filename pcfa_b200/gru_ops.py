@@ -9,11 +9,23 @@ from torch.autograd import Function
 from . import _lib
 
 
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _check(*ts, name):
+    for t in ts:
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"{name}: expected CUDA float32 tensors (pcfa_b200 has no CPU path)")
+
+
 class _Gates(Function):
     @staticmethod
     def forward(ctx, zr, h):
-        zr, h = zr.contiguous(), h.contiguous()
-        _lib.require_cuda(zr, h, name="gru_gates")
+        cl = _is_cl(h)
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        zr, h = zr.contiguous(memory_format=fmt), h.contiguous(memory_format=fmt)
+        _check(zr, h, name="gru_gates")
         B, C = h.shape[0], h.shape[1]
         if zr.shape[1] != 2 * C or zr.shape[0] != B or zr.shape[2:] != h.shape[2:]:
             raise RuntimeError(f"gru_gates: zr {tuple(zr.shape)} does not match h {tuple(h.shape)}")
@@ -21,8 +33,9 @@ class _Gates(Function):
         z, r, rh = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
         lib = _lib.load()
         _lib.check(lib.pcfa_gru_gates_forward(_lib.ptr(zr), _lib.ptr(h), _lib.ptr(z), _lib.ptr(r), _lib.ptr(rh), B, n,
-                                              _lib.stream()), "pcfa_gru_gates_forward")
+                                              C if cl else 0, _lib.stream()), "pcfa_gru_gates_forward")
         ctx.save_for_backward(z, r, h)
+        ctx.cl = cl
         return z, rh
 
     @staticmethod
@@ -30,21 +43,25 @@ class _Gates(Function):
         z, r, h = ctx.saved_tensors
         B = h.shape[0]
         n = h.numel() // B
-        gz = None if gz is None else gz.contiguous()
-        grh = None if grh is None else grh.contiguous()
-        gzr = torch.empty(B, 2 * h.shape[1], *h.shape[2:], device=h.device, dtype=h.dtype)
+        fmt = torch.channels_last if ctx.cl else torch.contiguous_format
+        gz = None if gz is None else gz.contiguous(memory_format=fmt)
+        grh = None if grh is None else grh.contiguous(memory_format=fmt)
+        gzr = torch.empty((B, 2 * h.shape[1], *h.shape[2:]), device=h.device, dtype=h.dtype, memory_format=fmt)
         gh = torch.empty_like(h)
         lib = _lib.load()
         _lib.check(lib.pcfa_gru_gates_backward(_lib.ptr(z), _lib.ptr(r), _lib.ptr(h), _lib.ptr(gz), _lib.ptr(grh),
-                                               _lib.ptr(gzr), _lib.ptr(gh), B, n, _lib.stream()), "pcfa_gru_gates_backward")
+                                               _lib.ptr(gzr), _lib.ptr(gh), B, n, h.shape[1] if ctx.cl else 0,
+                                               _lib.stream()), "pcfa_gru_gates_backward")
         return gzr, gh
 
 
 class _Blend(Function):
     @staticmethod
     def forward(ctx, z, q_pre, h):
-        z, q_pre, h = z.contiguous(), q_pre.contiguous(), h.contiguous()
-        _lib.require_cuda(z, q_pre, h, name="gru_blend")
+        fmt = torch.channels_last if _is_cl(h) else torch.contiguous_format      # element-wise: any common dense layout
+        z, q_pre, h = z.contiguous(memory_format=fmt), q_pre.contiguous(memory_format=fmt), h.contiguous(memory_format=fmt)
+        _check(z, q_pre, h, name="gru_blend")
+        ctx.fmt = fmt
         if not (z.shape == q_pre.shape == h.shape):
             raise RuntimeError("gru_blend: shape mismatch")
         q, hn = torch.empty_like(h), torch.empty_like(h)
@@ -57,7 +74,7 @@ class _Blend(Function):
     @staticmethod
     def backward(ctx, ghn):
         z, q, h = ctx.saved_tensors
-        ghn = ghn.contiguous()
+        ghn = ghn.contiguous(memory_format=ctx.fmt)
         gz, gq, gh = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
         lib = _lib.load()
         _lib.check(lib.pcfa_gru_blend_backward(_lib.ptr(z), _lib.ptr(q), _lib.ptr(h), _lib.ptr(ghn), _lib.ptr(gz),
@@ -77,3 +94,32 @@ def gru_blend(z: torch.Tensor, q_pre: torch.Tensor, h: torch.Tensor) -> torch.Te
 
 def usable(*ts: torch.Tensor) -> bool:
     return all(t.is_cuda and t.dtype == torch.float32 for t in ts) and not torch.is_autocast_enabled()
+
+
+class _CatCL(Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        import ctypes as C
+        xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
+        _check(*xs, name="cat_channels_last")
+        B, _, H, W = xs[0].shape
+        cs = [int(x.shape[1]) for x in xs]
+        out = torch.empty((B, sum(cs), H, W), device=xs[0].device, dtype=torch.float32, memory_format=torch.channels_last)
+        ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        chans = (C.c_int * len(xs))(*cs)
+        lib = _lib.load()
+        _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), len(xs), _lib.ptr(out),
+                                              B * H * W, _lib.stream()), "pcfa_cat_channels_last")
+        ctx.cs = cs
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(torch.split(g, ctx.cs, dim=1))
+
+
+def cat_channels(xs, channels_last: bool):
+    """torch.cat(xs, dim=1); channels-last inputs (B x C_k x H x W, at most four) go through one vectorised kernel."""
+    if channels_last and len(xs) <= 4 and all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 for x in xs):
+        return _CatCL.apply(*xs)
+    return torch.cat(xs, dim=1)

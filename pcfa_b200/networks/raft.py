@@ -208,20 +208,23 @@ def _zr_weights(cz: nn.Conv2d, cr: nn.Conv2d):
     cache = getattr(cz, "_pcfa_zr", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():
-            cache = (key, torch.cat([cz.weight, cr.weight], dim=0).contiguous(), torch.cat([cz.bias, cr.bias], dim=0).contiguous())
+            w = torch.cat([cz.weight, cr.weight], dim=0)
+            cl = cz.weight.is_contiguous(memory_format=torch.channels_last) and not cz.weight.is_contiguous()
+            w = w.contiguous(memory_format=torch.channels_last) if cl else w.contiguous()
+            cache = (key, w, torch.cat([cz.bias, cr.bias], dim=0).contiguous())
         cz._pcfa_zr = cache
     return cache[1], cache[2]
 
 
-def _gru_step(h, x, cz, cr, cq):
+def _gru_step(h, x, cz, cr, cq, cl=False):
     from .. import gru_ops
     frozen = not any(p.requires_grad for m in (cz, cr) for p in m.parameters())
     if gru_ops.usable(h, x) and frozen and cz.bias is not None and cr.bias is not None:
         # GPU path: one convolution for both gates, two fused element-wise launches (pcfa_b200/csrc/gru.cu)
-        hx = torch.cat([h, x], dim=1)
+        hx = gru_ops.cat_channels([h, x], cl)
         w, b = _zr_weights(cz, cr)
         z, rh = gru_ops.gru_gates(F.conv2d(hx, w, b, cz.stride, cz.padding), h)
-        return gru_ops.gru_blend(z, cq(torch.cat([rh, x], dim=1)), h)
+        return gru_ops.gru_blend(z, cq(gru_ops.cat_channels([rh, x], cl)), h)
     hx = torch.cat([h, x], dim=1)
     z = torch.sigmoid(cz(hx))
     r = torch.sigmoid(cr(hx))
@@ -249,9 +252,9 @@ class SepConvGRU(nn.Module):
             for gate in "zrq":
                 setattr(self, f"conv{gate}{tag}", nn.Conv2d(c, hidden_dim, k, padding=p))
 
-    def forward(self, h, x):
-        h = _gru_step(h, x, self.convz1, self.convr1, self.convq1)      # horizontal
-        return _gru_step(h, x, self.convz2, self.convr2, self.convq2)   # vertical
+    def forward(self, h, x, cl=False):
+        h = _gru_step(h, x, self.convz1, self.convr1, self.convq1, cl)      # horizontal
+        return _gru_step(h, x, self.convz2, self.convr2, self.convq2, cl)   # vertical
 
 
 class BasicMotionEncoder(nn.Module):
@@ -264,11 +267,12 @@ class BasicMotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
 
-    def forward(self, flow, corr):
+    def forward(self, flow, corr, cl=False):
+        from ..gru_ops import cat_channels
         cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
         flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
-        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
-        return torch.cat([out, flow], dim=1)
+        out = F.relu(self.conv(cat_channels([cor, flo], cl)))
+        return cat_channels([out, flow], cl)
 
 
 class SmallMotionEncoder(nn.Module):
@@ -296,9 +300,12 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(256, 64 * 9, 1))
 
-    def forward(self, net, inp, corr, flow, want_mask=True):
-        motion = self.encoder(flow, corr)
-        net = self.gru(net, torch.cat([inp, motion], dim=1))
+    def forward(self, net, inp, corr, flow, want_mask=True, cl=False):
+        """cl=True: every tensor is torch.channels_last (cuDNN's sm_100 kernels are NHWC-only; with NCHW activations
+        it converts around every convolution: 3 ms of the 11.8 ms RAFT closure)."""
+        from ..gru_ops import cat_channels
+        motion = self.encoder(flow, corr, cl)
+        net = self.gru(net, cat_channels([inp, motion], cl), cl)
         delta_flow = self.flow_head(net)
         mask = 0.25 * self.mask(net) if want_mask else None     # .25 "to balance gradients" (update.py:135)
         return net, mask, delta_flow
@@ -330,6 +337,7 @@ def upflow8(flow, mode="bilinear"):
 def convex_upsample(flow, mask):
     """[N,2,H,W] → [N,2,8H,8W] by a learned convex combination of the 3x3 neighbourhood (raft.py:72-83)."""
     N, _, H, W = flow.shape
+    flow, mask = flow.contiguous(), mask.contiguous()      # (channels-last update block: back to NCHW for the views)
     mask = torch.softmax(mask.view(N, 1, 9, 8, 8, H, W), dim=2)
     up = F.unfold(8 * flow, [3, 3], padding=1).view(N, 2, 9, 1, 1, H, W)
     up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
@@ -394,13 +402,25 @@ class RAFT(nn.Module):
             coords1 = coords1 + flow_init
         predictions = []
         flow_up = None
+        # NHWC update block (GPU, own CorrBlock, fp32): the lookup emits channels-last features directly
+        from ..corr_block import CorrBlock as _OwnCorrBlock
+        cl = (bool(getattr(self.update_block, "channels_last", False)) and dev_type == "cuda" and not amp
+              and isinstance(corr_fn, _OwnCorrBlock) and isinstance(self.update_block, BasicUpdateBlock))
+        if cl:
+            net = net.contiguous(memory_format=torch.channels_last)
+            inp = inp.contiguous(memory_format=torch.channels_last)
         for itr in range(iters):
             coords1 = coords1.detach()
-            corr = corr_fn(coords1)
+            corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
             flow = coords1 - coords0
             need_up = (not test_mode) or itr == iters - 1
             with torch.autocast(dev_type, enabled=amp):
-                net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
+                if cl:
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow.contiguous(memory_format=torch.channels_last),
+                                                                 want_mask=need_up, cl=True)
+                    delta_flow = delta_flow.contiguous()
+                else:
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
             coords1 = coords1 + delta_flow
             if need_up:
                 flow_up = upflow8(coords1 - coords0) if up_mask is None else convex_upsample(coords1 - coords0, up_mask)

@@ -172,3 +172,24 @@ def test_gma_autocast_config_runs(fp32_convs):
     flow = compute_flow(net, "GMA", a, i2.cuda())
     flow.float().abs().mean().backward()
     assert flow.shape == (1, 2, 128, 136) and torch.isfinite(a.grad).all()
+
+
+@pytest.mark.gpu
+def test_raft_channels_last_update_block_matches_nchw(fp32_convs):
+    """The NHWC update block (channels-last lookup, fused GRU, cat kernel) against the same network with NCHW
+    activations: identical arithmetic up to convolution algorithm choice."""
+    from pcfa_b200.adapter import build_network
+    from pcfa_b200.networks.weights import synthetic_pair
+    i1, i2 = synthetic_pair(3, 128, 160)
+    i1, i2 = i1.cuda(), i2.cuda()
+    flows, grads = [], []
+    for cl in (True, False):
+        net = build_network("RAFT", device="cuda", seed=0, gain=0.5, channels_last_update=cl)
+        a = i1.clone().requires_grad_(True)
+        _, flow = net(a, i2, iters=4, test_mode=True)
+        flow.square().mean().backward()
+        flows.append(flow.detach()); grads.append(a.grad.detach())
+    assert flows[0].is_contiguous()
+    assert_close(flows[0].cpu().numpy(), flows[1].cpu().numpy(), what="flow (NHWC vs NCHW update block)", rtol=1e-3, atol_rms=1e-3)
+    cos = float((grads[0] * grads[1]).sum() / (grads[0].norm() * grads[1].norm()))
+    assert cos > 0.999, cos
