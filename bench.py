@@ -130,7 +130,8 @@ def measured_traffic(entry_point):
     if not files:
         return None
     try:
-        return json.loads(files[-1].read_text())["entry_points"].get(entry_point)
+        ep = json.loads(files[-1].read_text())["entry_points"]
+        return ep.get(entry_point, ep.get(entry_point[:-3]) if entry_point.endswith("_cl") else None)
     except Exception:
         return None
 
@@ -277,7 +278,7 @@ def run_b200(args):
                                "algorithmic_bytes": top["algorithmic_bytes"], "avg_us": top["avg_us"],
                                "launches_per_step": top["launches_per_step"],
                                "peak_source": peak_src,
-                               "how": "CUDA events around each entry-point call in an eager pass of the same step, behind a device-side spin so host enqueue latency is excluded (graph replay cannot be event-bracketed per kernel)"}
+                               "how": "CUDA events around each entry-point call in an eager pass of the same step, behind a device-side spin so host enqueue latency is excluded, minus the duration of an empty event bracket (graph replay cannot be event-bracketed per kernel)"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, samples=args.cpu_samples)
         print(json.dumps(out), flush=True)

@@ -105,6 +105,8 @@ class _LibProxy:
             return fn
 
         def timed(*args):
+            global _bytes_hint
+            hint, _bytes_hint = _bytes_hint, None
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             # queue filler: a ~100 us device spin keeps the GPU busy while the host marshals the ctypes call and
@@ -114,9 +116,36 @@ class _LibProxy:
             e0.record()
             r = fn(*args)
             e1.record()
-            _profile.setdefault(name, []).append((e0, e1, args))
+            _profile.setdefault(name, []).append((e0, e1, args if hint is None else ("bytes", hint)))
             return r
         return timed
+
+
+_bytes_hint = None
+
+
+def hint_bytes(n: int) -> None:
+    """Algorithmic bytes of the NEXT profiled entry-point call, for callers whose arguments do not carry the shape
+    (pointer arrays).  Ignored when profiling is off."""
+    global _bytes_hint
+    if _profile is not None:
+        _bytes_hint = int(n)
+
+
+def event_overhead_us(n: int = 30) -> float:
+    """Median duration of an EMPTY event bracket behind the same device-side spin the profiled calls use: the part of
+    every bracketed measurement that is event bookkeeping, not kernel time (subtracted in profiling.kernel_table)."""
+    ts = []
+    for _ in range(n):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(200000)
+        e0.record()
+        e1.record()
+        ts.append((e0, e1))
+    torch.cuda.synchronize()
+    v = sorted(a.elapsed_time(b) * 1e3 for a, b in ts)
+    return v[len(v) // 2]
 
 
 def set_profile(store):

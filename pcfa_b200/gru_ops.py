@@ -108,6 +108,7 @@ class _CatCL(Function):
         ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
         chans = (C.c_int * len(xs))(*cs)
         lib = _lib.load()
+        _lib.hint_bytes(2 * 4 * out.numel())
         _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), len(xs), _lib.ptr(out),
                                               B * H * W, _lib.stream()), "pcfa_cat_channels_last")
         ctx.cs = cs

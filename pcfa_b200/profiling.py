@@ -21,6 +21,8 @@ def algorithmic_bytes(name: str, *, B: int, C: int, H: int, W: int, levels: int 
         return 4 * (2 * B * C * N + pyr)
     if name == "pcfa_corr_pyramid_backward":
         return 4 * (pyr + 4 * B * C * N)
+    if name.endswith("_cl"):                              # channels-last variants move the same bytes
+        name = name[:-3]
     if name == "pcfa_corr_lookup_forward":
         return 4 * B * N * (levels * F * F + levels * D * D + 2)
     if name == "pcfa_corr_lookup_backward":
@@ -36,6 +38,16 @@ def algorithmic_bytes(name: str, *, B: int, C: int, H: int, W: int, levels: int 
 
 def call_bytes(name: str, args):
     """Minimum HBM bytes of ONE call from its own arguments (entry points whose shape changes from call to call)."""
+    if len(args) == 2 and args[0] == "bytes":            # caller-provided (_lib.hint_bytes)
+        return args[1]
+    if name == "pcfa_gru_gates_forward":                 # (zr, h, z, r, rh, B, n, ...): read zr (2), h; write z, rh
+        return 4 * 5 * args[5] * args[6]
+    if name == "pcfa_gru_gates_backward":                # (z, r, h, gz, grh, gzr, gh, B, n, ...): read 5, write 3
+        return 4 * 8 * args[7] * args[8]
+    if name == "pcfa_gru_blend_forward":                 # (z, q_pre, h, q, h_new, numel, ...): read 3, write 2
+        return 4 * 5 * args[5]
+    if name == "pcfa_gru_blend_backward":                # (z, q, h, ghn, gz, gq, gh, numel, ...): read 4, write 3
+        return 4 * 7 * args[7]
     if name == "pcfa_instnorm_forward":                  # (x, y, stats, ws, B, C, H, W, ...): read x, write y
         return 4 * 2 * args[4] * args[5] * args[6] * args[7]
     if name == "pcfa_instnorm_backward":                 # (x, gy, stats, gx, ws, B, C, H, W, ...): read x, gy, write gx
@@ -56,9 +68,10 @@ def kernel_table(step_fn, n_steps: int, *, B: int, C: int, H: int, W: int, iters
         torch.cuda.synchronize()
     finally:
         _lib.set_profile(None)
+    overhead = _lib.event_overhead_us()
     rows = []
     for name, evs in store.items():
-        us = [a.elapsed_time(b) * 1e3 for a, b, _ in evs]
+        us = [max(a.elapsed_time(b) * 1e3 - overhead, 0.1) for a, b, _ in evs]
         per_step = len(us) / n_steps
         avg = sum(us) / len(us)
         ab = algorithmic_bytes(name, B=B, C=C, H=H, W=W, img_numel=img_numel, flow_numel=flow_numel)
