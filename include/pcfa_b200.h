@@ -307,6 +307,21 @@ int pcfa_gru_blend_forward(const float* z, const float* q_pre, const float* h, f
 int pcfa_gru_blend_backward(const float* z, const float* q, const float* h, const float* grad_h_new, float* grad_z,
                             float* grad_q_pre, float* grad_h, int64_t numel, pcfa_stream_t stream);
 
+/* Channels-last GRU halves with a hoisted pre-activation addend and concatenated outputs (NHWC update block):
+ *   gates_x : z = sigmoid(zr[:, :C] + addend[:, :C]), r = sigmoid(zr[:, C:] + addend[:, C:]), rhm = [r*h | m]
+ *   blend_x : q = tanh(q_pre + addend), h_new = (1-z)*h + z*q, hm = [h_new | m] (hm may be NULL)
+ * All tensors [npix][channels] (torch.channels_last), C and Cm multiples of 4, 16-byte aligned.  In the backward calls
+ * grad_rhm / grad_hm are the gradients of the concatenated outputs (their first C channels are consumed here, the tail
+ * is the caller's gradient of m); NULL gradient pointers mean zero. */
+int pcfa_gru_gates_x_forward(const float* zr, const float* addend, const float* h, const float* m, float* z, float* r, float* rhm,
+                             int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_gates_x_backward(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rhm,
+                              float* grad_zr, float* grad_h, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_blend_x_forward(const float* z, const float* q_pre, const float* addend, const float* h, const float* m, float* q,
+                             float* h_new, float* hm, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_blend_x_backward(const float* z, const float* q, const float* h, const float* grad_h_new, const float* grad_hm,
+                              float* grad_z, float* grad_q_pre, float* grad_h, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+
 /* Channel concatenation of up to four channels-last tensors [npix][C_k] -> [npix][sum C_k] (torch.cat(dim=1) of
  * torch.channels_last tensors, which ATen runs on a slow path). */
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,

@@ -64,6 +64,10 @@ SIGNATURES = {
     "pcfa_gru_gates_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_i, c_fp]),
     "pcfa_gru_blend_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_gru_blend_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
+    "pcfa_gru_gates_x_forward": (c_i, [c_fp] * 7 + [c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_gates_x_backward": (c_i, [c_fp] * 7 + [c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_blend_x_forward": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_blend_x_backward": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
     "pcfa_cat_channels_last": (c_i, [c_fp, c_fp, c_i, c_fp, c_i64, c_fp]),
     "pcfa_instnorm_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
 }

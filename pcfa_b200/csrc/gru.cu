@@ -120,6 +120,111 @@ cat_cl_kernel(const CatArgs a, float* __restrict__ out, int64_t npix, int vec) {
     }
 }
 
+// ------------------------------------------------------------------------------------ channels-last "x" variants
+// The NHWC update block hoists the iteration-invariant third of every GRU convolution (the context features `inp`)
+// out of the loop: P = conv(inp, W[:, inp slice]) + bias is computed once and enters here as an addend of the
+// pre-activations.  The kernels also write the next convolution's concatenated input directly — [r*h | m] from the
+// gates, [h' | m] from the blend (m = motion features, Cm channels) — so the two torch.cat launches per GRU step
+// disappear.  Pixel-major indexing: item = (pixel, channel quad) over C + Cm channels; quads >= C/4 copy m.
+struct GruX {
+    int C, Cm;
+    int64_t npix;
+};
+
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_gates_x_fwd_kernel(const float* __restrict__ zr, const float* __restrict__ P, const float* __restrict__ h,
+                       const float* __restrict__ m, float* __restrict__ z, float* __restrict__ r, float* __restrict__ rhm,
+                       GruX g) {
+    const int Q = (g.C + g.Cm) >> 2, QC = g.C >> 2;
+    const int64_t total = g.npix * Q;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / Q;
+        const int qd = (int)(e - p * Q);
+        float4* dst = reinterpret_cast<float4*>(rhm + p * (g.C + g.Cm)) + qd;
+        if (qd >= QC) { *dst = __ldg(reinterpret_cast<const float4*>(m + p * g.Cm) + (qd - QC)); continue; }
+        const float4 a = __ldg(reinterpret_cast<const float4*>(zr + p * 2 * g.C) + qd), pa = __ldg(reinterpret_cast<const float4*>(P + p * 2 * g.C) + qd);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(zr + p * 2 * g.C + g.C) + qd), pc = __ldg(reinterpret_cast<const float4*>(P + p * 2 * g.C + g.C) + qd);
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + p * g.C) + qd);
+        const float4 zz = make_float4(sigmoidf_(a.x + pa.x), sigmoidf_(a.y + pa.y), sigmoidf_(a.z + pa.z), sigmoidf_(a.w + pa.w));
+        const float4 rr = make_float4(sigmoidf_(c.x + pc.x), sigmoidf_(c.y + pc.y), sigmoidf_(c.z + pc.z), sigmoidf_(c.w + pc.w));
+        reinterpret_cast<float4*>(z + p * g.C)[qd] = zz;
+        reinterpret_cast<float4*>(r + p * g.C)[qd] = rr;
+        *dst = make_float4(rr.x * hv.x, rr.y * hv.y, rr.z * hv.z, rr.w * hv.w);
+    }
+}
+
+// grad_z [npix][C] (may be NULL), grad_rhm [npix][C+Cm] (may be NULL; its tail is the caller's grad of m, a view)
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_gates_x_bwd_kernel(const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ h,
+                       const float* __restrict__ gz, const float* __restrict__ grhm, float* __restrict__ gzr,
+                       float* __restrict__ gh, GruX g) {
+    const int QC = g.C >> 2;
+    const int64_t total = g.npix * QC;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / QC;
+        const int qd = (int)(e - p * QC);
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + p * g.C) + qd), rr = __ldg(reinterpret_cast<const float4*>(r + p * g.C) + qd);
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + p * g.C) + qd);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = gz ? __ldg(reinterpret_cast<const float4*>(gz + p * g.C) + qd) : zero;
+        const float4 b = grhm ? __ldg(reinterpret_cast<const float4*>(grhm + p * (g.C + g.Cm)) + qd) : zero;
+        reinterpret_cast<float4*>(gzr + p * 2 * g.C)[qd] =
+            make_float4(a.x * zz.x * (1.f - zz.x), a.y * zz.y * (1.f - zz.y), a.z * zz.z * (1.f - zz.z), a.w * zz.w * (1.f - zz.w));
+        reinterpret_cast<float4*>(gzr + p * 2 * g.C + g.C)[qd] =
+            make_float4(b.x * hv.x * rr.x * (1.f - rr.x), b.y * hv.y * rr.y * (1.f - rr.y), b.z * hv.z * rr.z * (1.f - rr.z),
+                        b.w * hv.w * rr.w * (1.f - rr.w));
+        reinterpret_cast<float4*>(gh + p * g.C)[qd] = make_float4(b.x * rr.x, b.y * rr.y, b.z * rr.z, b.w * rr.w);
+    }
+}
+
+// hm (may be NULL): [npix][C+Cm] = [h_new | m]
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_blend_x_fwd_kernel(const float* __restrict__ z, const float* __restrict__ qc, const float* __restrict__ P,
+                       const float* __restrict__ h, const float* __restrict__ m, float* __restrict__ q,
+                       float* __restrict__ hn, float* __restrict__ hm, GruX g) {
+    const int QC = g.C >> 2, Q = hm ? (g.C + g.Cm) >> 2 : QC;
+    const int64_t total = g.npix * Q;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / Q;
+        const int qd = (int)(e - p * Q);
+        if (qd >= QC) {
+            reinterpret_cast<float4*>(hm + p * (g.C + g.Cm))[qd] = __ldg(reinterpret_cast<const float4*>(m + p * g.Cm) + (qd - QC));
+            continue;
+        }
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + p * g.C) + qd), a = __ldg(reinterpret_cast<const float4*>(qc + p * g.C) + qd);
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(P + p * g.C) + qd), hv = __ldg(reinterpret_cast<const float4*>(h + p * g.C) + qd);
+        const float4 qq = make_float4(tanhf(a.x + pa.x), tanhf(a.y + pa.y), tanhf(a.z + pa.z), tanhf(a.w + pa.w));
+        const float4 o = make_float4((1.f - zz.x) * hv.x + zz.x * qq.x, (1.f - zz.y) * hv.y + zz.y * qq.y,
+                                     (1.f - zz.z) * hv.z + zz.z * qq.z, (1.f - zz.w) * hv.w + zz.w * qq.w);
+        reinterpret_cast<float4*>(q + p * g.C)[qd] = qq;
+        reinterpret_cast<float4*>(hn + p * g.C)[qd] = o;
+        if (hm) reinterpret_cast<float4*>(hm + p * (g.C + g.Cm))[qd] = o;
+    }
+}
+
+// total grad of h_new = ghn (may be NULL) + ghm[:, :C] (may be NULL)
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_blend_x_bwd_kernel(const float* __restrict__ z, const float* __restrict__ q, const float* __restrict__ h,
+                       const float* __restrict__ ghn, const float* __restrict__ ghm, float* __restrict__ gz,
+                       float* __restrict__ gq, float* __restrict__ gh, GruX g) {
+    const int QC = g.C >> 2;
+    const int64_t total = g.npix * QC;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / QC;
+        const int qd = (int)(e - p * QC);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = ghn ? __ldg(reinterpret_cast<const float4*>(ghn + p * g.C) + qd) : zero;
+        const float4 b = ghm ? __ldg(reinterpret_cast<const float4*>(ghm + p * (g.C + g.Cm)) + qd) : zero;
+        const float4 d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + p * g.C) + qd), qq = __ldg(reinterpret_cast<const float4*>(q + p * g.C) + qd);
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + p * g.C) + qd);
+        reinterpret_cast<float4*>(gz + p * g.C)[qd] = make_float4(d.x * (qq.x - hv.x), d.y * (qq.y - hv.y), d.z * (qq.z - hv.z), d.w * (qq.w - hv.w));
+        reinterpret_cast<float4*>(gq + p * g.C)[qd] = make_float4(d.x * zz.x * (1.f - qq.x * qq.x), d.y * zz.y * (1.f - qq.y * qq.y),
+                                                                  d.z * zz.z * (1.f - qq.z * qq.z), d.w * zz.w * (1.f - qq.w * qq.w));
+        reinterpret_cast<float4*>(gh + p * g.C)[qd] = make_float4(d.x * (1.f - zz.x), d.y * (1.f - zz.y), d.z * (1.f - zz.z), d.w * (1.f - zz.w));
+    }
+}
+
 static int gru_grid(int64_t n, int vec) {
     const int64_t per = (int64_t)GRU_THREADS * (vec ? 4 : 1);
     int64_t b = (n + per - 1) / per;
@@ -205,5 +310,51 @@ extern "C" int pcfa_cat_channels_last(const float* const* inputs, const int* cha
     const int64_t cap = (int64_t)kNumSMs * 8;
     if (blocks > cap) blocks = cap;
     cat_cl_kernel<<<(int)blocks, GRU_THREADS, 0, as_stream(stream)>>>(a, out, npix, vec);
+    return after_launch();
+}
+
+static int grux_check(int C, int Cm, int64_t npix, std::initializer_list<const void*> ps) {
+    if (C <= 0 || Cm < 0 || C % 4 || Cm % 4 || npix <= 0) return PCFA_E_BADARG;
+    for (const void* p : ps) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return PCFA_E_BADARG;
+    return PCFA_OK;
+}
+
+extern "C" int pcfa_gru_gates_x_forward(const float* zr, const float* addend, const float* h, const float* m, float* z, float* r,
+                                        float* rhm, int C, int Cm, int64_t npix, pcfa_stream_t stream) {
+    if (!zr || !addend || !h || !m || !z || !r || !rhm) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {zr, addend, h, m, z, r, rhm}));
+    const GruX g{C, Cm, npix};
+    gru_gates_x_fwd_kernel<<<gru_grid(npix * (C + Cm), 1), GRU_THREADS, 0, as_stream(stream)>>>(zr, addend, h, m, z, r, rhm, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_gates_x_backward(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rhm,
+                                         float* grad_zr, float* grad_h, int C, int Cm, int64_t npix, pcfa_stream_t stream) {
+    if (!z || !r || !h || !grad_zr || !grad_h) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {z, r, h, grad_z, grad_rhm, grad_zr, grad_h}));
+    const GruX g{C, Cm, npix};
+    gru_gates_x_bwd_kernel<<<gru_grid(npix * C, 1), GRU_THREADS, 0, as_stream(stream)>>>(z, r, h, grad_z, grad_rhm, grad_zr, grad_h, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_blend_x_forward(const float* z, const float* q_pre, const float* addend, const float* h, const float* m,
+                                        float* q, float* h_new, float* hm /* may be NULL */, int C, int Cm, int64_t npix,
+                                        pcfa_stream_t stream) {
+    if (!z || !q_pre || !addend || !h || !q || !h_new || (hm && !m)) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {z, q_pre, addend, h, m, q, h_new, hm}));
+    const GruX g{C, Cm, npix};
+    gru_blend_x_fwd_kernel<<<gru_grid(npix * (hm ? C + Cm : C), 1), GRU_THREADS, 0, as_stream(stream)>>>(z, q_pre, addend, h, m, q,
+                                                                                                         h_new, hm, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_blend_x_backward(const float* z, const float* q, const float* h, const float* grad_h_new, const float* grad_hm,
+                                         float* grad_z, float* grad_q_pre, float* grad_h, int C, int Cm, int64_t npix,
+                                         pcfa_stream_t stream) {
+    if (!z || !q || !h || !grad_z || !grad_q_pre || !grad_h) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {z, q, h, grad_h_new, grad_hm, grad_z, grad_q_pre, grad_h}));
+    const GruX g{C, Cm, npix};
+    gru_blend_x_bwd_kernel<<<gru_grid(npix * C, 1), GRU_THREADS, 0, as_stream(stream)>>>(z, q, h, grad_h_new, grad_hm, grad_z, grad_q_pre,
+                                                                                        grad_h, g);
     return after_launch();
 }

@@ -124,3 +124,77 @@ def cat_channels(xs, channels_last: bool):
     if channels_last and len(xs) <= 4 and all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 for x in xs):
         return _CatCL.apply(*xs)
     return torch.cat(xs, dim=1)
+
+
+_CL = torch.channels_last
+
+
+class _GatesX(Function):
+    """z, [r*h | m] from zr + addend (channels-last; see pcfa_gru_gates_x_forward)."""
+
+    @staticmethod
+    def forward(ctx, zr, addend, h, m):
+        zr, addend, h, m = (t.contiguous(memory_format=_CL) for t in (zr, addend, h, m))
+        _check(zr, addend, h, m, name="gru_gates_x")
+        B, C, H, W = h.shape
+        Cm = m.shape[1]
+        z, r = torch.empty_like(h), torch.empty_like(h)
+        rhm = torch.empty((B, C + Cm, H, W), device=h.device, dtype=h.dtype, memory_format=_CL)
+        lib = _lib.load()
+        _lib.check(lib.pcfa_gru_gates_x_forward(_lib.ptr(zr), _lib.ptr(addend), _lib.ptr(h), _lib.ptr(m), _lib.ptr(z), _lib.ptr(r),
+                                                _lib.ptr(rhm), C, Cm, B * H * W, _lib.stream()), "pcfa_gru_gates_x_forward")
+        ctx.save_for_backward(z, r, h)
+        ctx.cm = Cm
+        return z, rhm
+
+    @staticmethod
+    def backward(ctx, gz, grhm):
+        z, r, h = ctx.saved_tensors
+        B, C, H, W = h.shape
+        gz = None if gz is None else gz.contiguous(memory_format=_CL)
+        grhm = None if grhm is None else grhm.contiguous(memory_format=_CL)
+        gzr = torch.empty((B, 2 * C, H, W), device=h.device, dtype=h.dtype, memory_format=_CL)
+        gh = torch.empty_like(h)
+        lib = _lib.load()
+        _lib.check(lib.pcfa_gru_gates_x_backward(_lib.ptr(z), _lib.ptr(r), _lib.ptr(h), _lib.ptr(gz), _lib.ptr(grhm), _lib.ptr(gzr),
+                                                 _lib.ptr(gh), C, ctx.cm, B * H * W, _lib.stream()), "pcfa_gru_gates_x_backward")
+        return gzr, gzr, gh, (None if grhm is None else grhm[:, C:])
+
+
+class _BlendX(Function):
+    """h_new (and [h_new | m]) from z, q_pre + addend, h (channels-last; see pcfa_gru_blend_x_forward)."""
+
+    @staticmethod
+    def forward(ctx, z, q_pre, addend, h, m, make_hm):
+        z, q_pre, addend, h, m = (t.contiguous(memory_format=_CL) for t in (z, q_pre, addend, h, m))
+        _check(z, q_pre, addend, h, m, name="gru_blend_x")
+        B, C, H, W = h.shape
+        Cm = m.shape[1]
+        q, hn = torch.empty_like(h), torch.empty_like(h)
+        hm = torch.empty((B, C + Cm, H, W), device=h.device, dtype=h.dtype, memory_format=_CL) if make_hm else None
+        lib = _lib.load()
+        _lib.check(lib.pcfa_gru_blend_x_forward(_lib.ptr(z), _lib.ptr(q_pre), _lib.ptr(addend), _lib.ptr(h), _lib.ptr(m), _lib.ptr(q),
+                                                _lib.ptr(hn), _lib.ptr(hm), C, Cm, B * H * W, _lib.stream()), "pcfa_gru_blend_x_forward")
+        ctx.save_for_backward(z, q, h)
+        ctx.cm, ctx.make_hm = Cm, bool(make_hm)
+        return (hn, hm) if make_hm else hn
+
+    @staticmethod
+    def backward(ctx, ghn, ghm=None):
+        z, q, h = ctx.saved_tensors
+        B, C, H, W = h.shape
+        ghn = None if ghn is None else ghn.contiguous(memory_format=_CL)
+        ghm = None if ghm is None else ghm.contiguous(memory_format=_CL)
+        gz, gq, gh = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        lib = _lib.load()
+        _lib.check(lib.pcfa_gru_blend_x_backward(_lib.ptr(z), _lib.ptr(q), _lib.ptr(h), _lib.ptr(ghn), _lib.ptr(ghm), _lib.ptr(gz),
+                                                 _lib.ptr(gq), _lib.ptr(gh), C, ctx.cm, B * H * W, _lib.stream()), "pcfa_gru_blend_x_backward")
+        return gz, gq, gq, gh, (None if ghm is None else ghm[:, C:]), None
+
+
+def gru_gates_x(zr, addend, h, m):
+    return _GatesX.apply(zr, addend, h, m)
+
+
+def gru_blend_x(z, q_pre, addend, h, m, make_hm: bool):
+    return _BlendX.apply(z, q_pre, addend, h, m, make_hm)

@@ -256,6 +256,43 @@ class SepConvGRU(nn.Module):
         h = _gru_step(h, x, self.convz1, self.convr1, self.convq1, cl)      # horizontal
         return _gru_step(h, x, self.convz2, self.convr2, self.convq2, cl)   # vertical
 
+    # ---- NHWC fast path: x = [inp | motion] and inp is the same in every iteration, so its share of the four
+    # convolutions is computed once per forward pass ("hoisted") and enters the fused element-wise kernels as an addend
+    def _split_weights(self, ci):
+        convs = [self.convz1, self.convr1, self.convq1, self.convz2, self.convr2, self.convq2]
+        key = tuple((t.data_ptr(), t._version) for c in convs for t in (c.weight, c.bias)) + (ci,)
+        cache = getattr(self, "_pcfa_split", None)
+        if cache is None or cache[0] != key:
+            ch = self.convz1.out_channels
+            out = []
+            with torch.no_grad():
+                for cz, cr, cq in ((self.convz1, self.convr1, self.convq1), (self.convz2, self.convr2, self.convq2)):
+                    step = []
+                    for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
+                        w_hm = torch.cat([w[:, :ch], w[:, ch + ci:]], 1).contiguous(memory_format=torch.channels_last)
+                        w_in = w[:, ch:ch + ci].contiguous(memory_format=torch.channels_last)
+                        step.append((w_hm, w_in, b.contiguous()))
+                    out.append((step, cz.padding))
+            cache = (key, out)
+            self._pcfa_split = cache
+        return cache[1]
+
+    def hoisted(self, inp):
+        """[(W_hm_zr, P_zr, W_hm_q, P_q, padding)] for the horizontal and the vertical step; P = conv(inp, W_inp) + bias."""
+        res = []
+        for (zr, q), pad in self._split_weights(inp.shape[1]):
+            res.append((zr[0], F.conv2d(inp, zr[1], zr[2], 1, pad), q[0], F.conv2d(inp, q[1], q[2], 1, pad), pad))
+        return res
+
+    def forward_x(self, h, motion, hoist):
+        from ..gru_ops import cat_channels, gru_blend_x, gru_gates_x
+        (wzr1, pzr1, wq1, pq1, pad1), (wzr2, pzr2, wq2, pq2, pad2) = hoist
+        hm = cat_channels([h, motion], True)
+        z, rhm = gru_gates_x(F.conv2d(hm, wzr1, None, 1, pad1), pzr1, h, motion)
+        h, hm = gru_blend_x(z, F.conv2d(rhm, wq1, None, 1, pad1), pq1, h, motion, True)
+        z, rhm = gru_gates_x(F.conv2d(hm, wzr2, None, 1, pad2), pzr2, h, motion)
+        return gru_blend_x(z, F.conv2d(rhm, wq2, None, 1, pad2), pq2, h, motion, False)
+
 
 class BasicMotionEncoder(nn.Module):
     def __init__(self, corr_levels, corr_radius):
@@ -300,12 +337,15 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(256, 64 * 9, 1))
 
-    def forward(self, net, inp, corr, flow, want_mask=True, cl=False):
+    def forward(self, net, inp, corr, flow, want_mask=True, cl=False, hoist=None):
         """cl=True: every tensor is torch.channels_last (cuDNN's sm_100 kernels are NHWC-only; with NCHW activations
         it converts around every convolution: 3 ms of the 11.8 ms RAFT closure)."""
         from ..gru_ops import cat_channels
         motion = self.encoder(flow, corr, cl)
-        net = self.gru(net, cat_channels([inp, motion], cl), cl)
+        if hoist is not None:
+            net = self.gru.forward_x(net, motion, hoist)
+        else:
+            net = self.gru(net, cat_channels([inp, motion], cl), cl)
         delta_flow = self.flow_head(net)
         mask = 0.25 * self.mask(net) if want_mask else None     # .25 "to balance gradients" (update.py:135)
         return net, mask, delta_flow
@@ -406,9 +446,13 @@ class RAFT(nn.Module):
         from ..corr_block import CorrBlock as _OwnCorrBlock
         cl = (bool(getattr(self.update_block, "channels_last", False)) and dev_type == "cuda" and not amp
               and isinstance(corr_fn, _OwnCorrBlock) and isinstance(self.update_block, BasicUpdateBlock))
+        hoist = None
         if cl:
             net = net.contiguous(memory_format=torch.channels_last)
             inp = inp.contiguous(memory_format=torch.channels_last)
+            frozen = not any(p.requires_grad for p in self.update_block.gru.parameters())
+            if frozen and net.shape[1] % 4 == 0 and inp.shape[1] % 4 == 0:
+                hoist = self.update_block.gru.hoisted(inp)
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
@@ -417,7 +461,7 @@ class RAFT(nn.Module):
             with torch.autocast(dev_type, enabled=amp):
                 if cl:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow.contiguous(memory_format=torch.channels_last),
-                                                                 want_mask=need_up, cl=True)
+                                                                 want_mask=need_up, cl=True, hoist=hoist)
                     delta_flow = delta_flow.contiguous()
                 else:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)

@@ -40,6 +40,16 @@ def call_bytes(name: str, args):
     """Minimum HBM bytes of ONE call from its own arguments (entry points whose shape changes from call to call)."""
     if len(args) == 2 and args[0] == "bytes":            # caller-provided (_lib.hint_bytes)
         return args[1]
+    if name == "pcfa_gru_gates_x_forward":               # (zr, P, h, m, z, r, rhm, C, Cm, npix): r is not counted
+        C, Cm, n = args[7], args[8], args[9]
+        return 4 * n * (7 * C + 2 * Cm)
+    if name == "pcfa_gru_gates_x_backward":              # (z, r, h, gz, grhm, gzr, gh, C, Cm, npix)
+        return 4 * args[9] * 8 * args[7]
+    if name == "pcfa_gru_blend_x_forward":               # (z, q_pre, P, h, m, q, hn, hm, C, Cm, npix)
+        C, Cm, n = args[8], args[9], args[10]
+        return 4 * n * (6 * C + (C + 2 * Cm if args[7] is not None else 0))
+    if name == "pcfa_gru_blend_x_backward":              # (z, q, h, ghn, ghm, gz, gq, gh, C, Cm, npix)
+        return 4 * args[10] * 8 * args[8]
     if name == "pcfa_gru_gates_forward":                 # (zr, h, z, r, rh, B, n, ...): read zr (2), h; write z, rh
         return 4 * 5 * args[5] * args[6]
     if name == "pcfa_gru_gates_backward":                # (z, r, h, gz, grh, gzr, gh, B, n, ...): read 5, write 3
