@@ -17,6 +17,7 @@ one L-BFGS instance for the whole run).  Differences in mechanism, not in the op
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass, field
 
 import torch
@@ -190,7 +191,7 @@ def pcfa_attack(model, net_name, image1, image2, *, steps=20, delta_bound=0.005,
                 res.delta1_best, res.delta2_best = d1.detach().clone(), d2.detach().clone()
                 res.flow_best = flow_pred.detach().clone()
         res.history.append(dict(step=step, aee_adv_tgt=aee_adv_tgt, aee_adv_pred=aee_adv_pred, l2_delta12=l2_12,
-                                loss=float(fo.terms[0])))
+                                loss=float(fo.terms[0]), closure_evals=counter[0], t=time.perf_counter()))
     res.closure_evals = counter[0]
     return res
 

@@ -75,17 +75,15 @@ for name in only:
             n0 = _lib.launch_count(); fo.evaluate(v1, v2, ev.g1, ev.g2); torch.cuda.synchronize()
             row["pcfa_launches_per_closure"] = _lib.launch_count() - n0
             del ev, fo
-            # outer steps (host L-BFGS around graph replays): difference of a 4-step and a 1-step run, so that set-up
-            # (initial prediction, graph capture) cancels
-            def run(steps):
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                r = pcfa_attack(model, net_name, i1, i2, steps=steps, joint_perturbation=joint, boxconstraint=box, iters=iters, keep_best=False)
-                torch.cuda.synchronize()
-                return time.perf_counter() - t0, r.closure_evals
-            run(4)                                                   # warm: cuDNN autotuning for every shape on the path
-            t1 = min(run(1)[0] for _ in range(2)); n1 = run(1)[1]
-            t4, n4 = min((run(4) for _ in range(2)), key=lambda r: r[0])
-            row.update(outer_step_s=(t4 - t1) / 3, closures_per_outer_step=(n4 - n1) / 3, setup_s=t1 - (t4 - t1) / 3)
+            # outer steps (host L-BFGS around graph replays): wall clock between the per-step metric syncs of ONE
+            # 5-step run (pcfa_attack stamps every outer step after its D2H of the metrics); the first step is dropped
+            pcfa_attack(model, net_name, i1, i2, steps=2, joint_perturbation=joint, boxconstraint=box, iters=iters, keep_best=False)
+            r = pcfa_attack(model, net_name, i1, i2, steps=5, joint_perturbation=joint, boxconstraint=box, iters=iters, keep_best=False)
+            hs = r.history
+            dts = [hs[k]["t"] - hs[k - 1]["t"] for k in range(1, len(hs))]
+            ncl = [hs[k]["closure_evals"] - hs[k - 1]["closure_evals"] for k in range(1, len(hs))]
+            row.update(outer_step_s=statistics.median(dts), closures_per_outer_step=statistics.median(ncl),
+                       host_overhead_frac=round(1.0 - statistics.median(ncl) * row["closure_ms"] * 1e-3 / statistics.median(dts), 3))
     except Exception as e:                                           # keep going: one config must not hide the others
         row["error"] = repr(e)[:300]
     row["max_mem_GB"] = round(torch.cuda.max_memory_allocated() / 2**30, 2)
