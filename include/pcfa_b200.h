@@ -327,6 +327,22 @@ int pcfa_gru_blend_x_backward(const float* z, const float* q, const float* h, co
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,
                            pcfa_stream_t stream);
 
+/* --------------------------------------------------------------------------- on-device L-BFGS
+ * The vector algebra of torch.optim.LBFGS.step (torch/optim/lbfgs.py; the reference's optimiser, attack_PCFA.py:97,114)
+ * without its ~4*history ATen launches per iteration.  History: ring buffers S, Y of [history_capacity][n] floats.
+ *   pcfa_lbfgs_store_pair : y = grad - grad_prev -> y_slot, s = t*d -> s_slot, grad_prev <- grad;
+ *                           scalars_out = { <y,s>, <y,y> } (device floats)
+ *   pcfa_lbfgs_direction  : two-loop recursion over the `num_old` pairs starting at ring index `start` (oldest first),
+ *                           ro[slot] = 1/<y,s>, *h_diag = <y,s>/<y,y> of the newest pair (device floats);
+ *                           d <- -H*grad;  scalars_out = { <grad,d>, max|d| }.  One cooperative launch.
+ * workspace: pcfa_lbfgs_workspace_bytes(). */
+int64_t pcfa_lbfgs_workspace_bytes(void);
+int pcfa_lbfgs_store_pair(const float* grad, float* grad_prev, const float* d, float t, float* s_slot, float* y_slot,
+                          float* scalars_out, void* workspace, int64_t n, pcfa_stream_t stream);
+int pcfa_lbfgs_direction(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag, float* d,
+                         float* scalars_out, void* workspace, int64_t n, int history_capacity, int start, int num_old,
+                         pcfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

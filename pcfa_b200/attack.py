@@ -79,10 +79,10 @@ class PairResult:
 class GraphedEvaluate:
     """FusedObjective.evaluate behind a CUDA graph: variables and gradients live in static buffers."""
 
-    def __init__(self, fo: J.FusedObjective, var1, var2, use_graph=True, warmup=3):
+    def __init__(self, fo: J.FusedObjective, var1, var2, use_graph=True, warmup=3, g1=None, g2=None):
         self.fo, self.var1, self.var2 = fo, var1, var2
-        self.g1 = torch.empty_like(var1)
-        self.g2 = None if var2 is None else torch.empty_like(var2)
+        self.g1 = torch.empty_like(var1) if g1 is None else g1
+        self.g2 = None if var2 is None else (torch.empty_like(var2) if g2 is None else g2)
         self.graph = None
         if use_graph:
             side = torch.cuda.Stream()
@@ -114,7 +114,7 @@ def _net_forward(model, net_name, iters=None):
 def pcfa_attack(model, net_name, image1, image2, *, steps=20, delta_bound=0.005, mu=-1., target='zero',
                 loss='aee', joint_perturbation=False, boxconstraint='change_of_variables', eps_box=1e-7,
                 custom_target_path="", use_graph=True, iters=None, lbfgs_max_iter=10, keep_best=True,
-                reduce_hook=None):
+                reduce_hook=None, lbfgs="device"):
     """One image pair ([B,3,H,W] in [0,255] on the device).  Returns a PairResult.
     Follows attack_PCFA.py:40-294 step for step (see module docstring for the mechanical differences)."""
     device = image1.device
@@ -146,22 +146,46 @@ def pcfa_attack(model, net_name, image1, image2, *, steps=20, delta_bound=0.005,
     fo.target.copy_(get_target(target, flow_init, custom_target_path))
     res = PairResult(aee_tgt=float(avg_epe(fo.target, flow_init)))
 
-    ev = GraphedEvaluate(fo, var1, var2, use_graph=use_graph)
-    params = [var1] if var2 is None else [var1, var2]
-    for p in params:
-        p.requires_grad_(True)
-    optimizer = torch.optim.LBFGS(params, max_iter=lbfgs_max_iter)
     counter = [0]
-
-    def closure():
-        counter[0] += 1
-        loss_t = ev()
-        if reduce_hook is not None:
-            loss_t = reduce_hook(loss_t, ev.g1, ev.g2)
-        var1.grad = ev.g1
+    if lbfgs == "device":
+        # f-1: variables and gradients are slices of two flat device buffers; pcfa_b200.lbfgs.DeviceLBFGS runs
+        # torch.optim.LBFGS's update rule on them in three launches per iteration
+        from .lbfgs import DeviceLBFGS
+        n1 = var1.numel()
+        n2 = 0 if var2 is None else var2.numel()
+        flat_p, flat_g = torch.empty(n1 + n2, device=device), torch.zeros(n1 + n2, device=device)
+        flat_p[:n1].copy_(var1.reshape(-1))
+        var1 = flat_p[:n1].view_as(var1)
+        g1, g2 = flat_g[:n1].view_as(var1), None
         if var2 is not None:
-            var2.grad = ev.g2
-        return loss_t
+            flat_p[n1:].copy_(var2.reshape(-1))
+            var2 = flat_p[n1:].view_as(var2)
+            g2 = flat_g[n1:].view_as(var2)
+        ev = GraphedEvaluate(fo, var1, var2, use_graph=use_graph, g1=g1, g2=g2)
+        optimizer = DeviceLBFGS(flat_p, flat_g, max_iter=lbfgs_max_iter)
+
+        def closure():
+            counter[0] += 1
+            loss_t = ev()
+            if reduce_hook is not None:
+                loss_t = reduce_hook(loss_t, ev.g1, ev.g2)
+            return loss_t
+    else:
+        ev = GraphedEvaluate(fo, var1, var2, use_graph=use_graph)
+        params = [var1] if var2 is None else [var1, var2]
+        for p in params:
+            p.requires_grad_(True)
+        optimizer = torch.optim.LBFGS(params, max_iter=lbfgs_max_iter)
+
+        def closure():
+            counter[0] += 1
+            loss_t = ev()
+            if reduce_hook is not None:
+                loss_t = reduce_hook(loss_t, ev.g1, ev.g2)
+            var1.grad = ev.g1
+            if var2 is not None:
+                var2.grad = ev.g2
+            return loss_t
 
     below = False
     for step in range(steps):
