@@ -279,6 +279,22 @@ def run_b200(args):
                                "launches_per_step": top["launches_per_step"],
                                "peak_source": peak_src,
                                "how": "CUDA events around each entry-point call in an eager pass of the same step, behind a device-side spin so host enqueue latency is excluded, minus the duration of an empty event bracket (graph replay cannot be event-bracketed per kernel)"}
+        if world == 1:
+            # outer L-BFGS steps per second of the attack loop itself (10 closures + one
+            # re-prediction + the optimiser's vector algebra per step), pcfa_attack on the same pair
+            try:
+                import time as _time
+                from pcfa_b200.attack import pcfa_attack
+                a1, a2 = i1_host.to(device), i2_host.to(device)
+                pcfa_attack(net, "RAFT", a1, a2, steps=1, iters=12, keep_best=False)
+                r = pcfa_attack(net, "RAFT", a1, a2, steps=5, iters=12, keep_best=False)
+                hs = r.history
+                dts = sorted(hs[k]["t"] - hs[k - 1]["t"] for k in range(1, len(hs)))
+                ncl = sorted(hs[k]["closure_evals"] - hs[k - 1]["closure_evals"] for k in range(1, len(hs)))
+                out["attack"] = {"outer_steps_per_s": round(1.0 / dts[len(dts) // 2], 3), "outer_step_ms": round(1e3 * dts[len(dts) // 2], 2),
+                                 "closures_per_outer_step": ncl[len(ncl) // 2], "optimizer": "pcfa_b200.lbfgs.DeviceLBFGS (torch.optim.LBFGS semantics, max_iter 10)"}
+            except Exception as e:                                   # the headline line must not depend on it
+                out["attack"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, samples=args.cpu_samples)
         print(json.dumps(out), flush=True)

@@ -104,6 +104,33 @@ class GraphedEvaluate:
         return self.fo.terms[0]
 
 
+class GraphedPredict:
+    """FusedObjective.predict(var1, var2, want_delta=True) behind a CUDA graph (the per-outer-step re-prediction of
+    attack_PCFA.py:212-224 is ~600 eager launches otherwise: as long as ten graphed closure evaluations' worth of
+    host time)."""
+
+    def __init__(self, fo: J.FusedObjective, var1, var2, use_graph=True):
+        self.fo, self.var1, self.var2 = fo, var1, var2
+        self.graph, self.out = None, None
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                fo.predict(var1, var2, want_delta=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.out = fo.predict(var1, var2, want_delta=True)
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.out
+        with torch.no_grad():
+            return self.fo.predict(self.var1, self.var2, want_delta=True)
+
+
 def _net_forward(model, net_name, iters=None):
     kw = {}
     if iters is not None and net_name in ("RAFT",):
@@ -188,10 +215,11 @@ def pcfa_attack(model, net_name, image1, image2, *, steps=20, delta_bound=0.005,
             return loss_t
 
     below = False
+    repredict = GraphedPredict(fo, var1.detach(), None if var2 is None else var2.detach(), use_graph=use_graph)
     for step in range(steps):
         optimizer.step(closure)
         with torch.no_grad():
-            flow_pred = padder.unpad(fo.predict(var1.detach(), None if var2 is None else var2.detach(), want_delta=True))
+            flow_pred = padder.unpad(repredict())
             d1, d2 = fo.delta1, fo.delta2 if fo.delta2 is not None else fo.delta1
             stats = torch.stack([avg_epe(flow_pred, fo.target), avg_epe(flow_pred, flow_init),
                                  d1.pow(2).sum(), d2.pow(2).sum()]).tolist()     # one D2H per outer step
