@@ -255,7 +255,7 @@ class UniversalAttack:
     all-reduces [grad_delta1 | grad_delta2 | loss] (sum, then / world_size)."""
 
     def __init__(self, model, net_name, image_shape, device, *, delta_bound=0.005, mu=-1., target='zero', loss='aee',
-                 joint_perturbation=False, eps_box=1e-7, iters=None, lbfgs_max_iter=10, use_graph=False):
+                 joint_perturbation=False, eps_box=1e-7, iters=None, lbfgs_max_iter=10, use_graph=False, lbfgs="device"):
         self.model, self.net_name, self.device = model, net_name, device
         self.delta_bound, self.target, self.loss = delta_bound, target, loss
         self.mu = resolve_mu(mu, delta_bound, target)
@@ -264,12 +264,25 @@ class UniversalAttack:
         dummy = torch.zeros(1, 3, *image_shape, device=device)
         self.padder, (padded,) = preprocess_img(net_name, dummy)
         chw = padded.shape[1:]
-        self.delta1 = torch.zeros(chw, device=device, requires_grad=True)
-        self.delta2 = None if joint_perturbation else torch.zeros(chw, device=device, requires_grad=True)
-        params = [self.delta1] if self.delta2 is None else [self.delta1, self.delta2]
-        self.optimizer = torch.optim.LBFGS(params, max_iter=lbfgs_max_iter)
-        n = sum(p.numel() for p in params)
+        n1 = int(torch.Size(chw).numel())
+        n = n1 if joint_perturbation else 2 * n1
         self.flat = torch.zeros(n + 1, device=device)            # fused all-reduce buffer [grads | loss]
+        self.device_lbfgs = lbfgs == "device" and torch.device(device).type == "cuda"
+        if self.device_lbfgs:
+            # f-1: deltas are slices of one flat parameter buffer, their gradients slices of the all-reduce buffer
+            from .lbfgs import DeviceLBFGS
+            self.flat_p = torch.zeros(n, device=device)
+            self.delta1 = self.flat_p[:n1].view(chw)
+            self.delta2 = None if joint_perturbation else self.flat_p[n1:].view(chw)
+            self.g1 = self.flat[:n1].view(chw)
+            self.g2 = None if joint_perturbation else self.flat[n1:n].view(chw)
+            self.optimizer = DeviceLBFGS(self.flat_p, self.flat[:n], max_iter=lbfgs_max_iter)
+        else:
+            self.delta1 = torch.zeros(chw, device=device, requires_grad=True)
+            self.delta2 = None if joint_perturbation else torch.zeros(chw, device=device, requires_grad=True)
+            params = [self.delta1] if self.delta2 is None else [self.delta1, self.delta2]
+            self.optimizer = torch.optim.LBFGS(params, max_iter=lbfgs_max_iter)
+            self.g1 = self.g2 = None
         self.closure_evals = 0
 
     def _dist(self):
@@ -294,16 +307,17 @@ class UniversalAttack:
         fo.target.copy_(get_target(self.target, flow_init))
         d1 = self.delta1.detach()
         d2 = None if self.delta2 is None else self.delta2.detach()
-        ev = GraphedEvaluate(fo, d1, d2, use_graph=self.use_graph)
+        ev = GraphedEvaluate(fo, d1, d2, use_graph=self.use_graph, g1=self.g1, g2=self.g2)
         dist = self._dist()
         def closure():
             self.closure_evals += 1
             loss_t = ev()
             if dist is not None:
                 loss_t = pack_reduce_unpack(self.flat, loss_t, ev.g1, ev.g2)
-            self.delta1.grad = ev.g1
-            if self.delta2 is not None:
-                self.delta2.grad = ev.g2
+            if not self.device_lbfgs:
+                self.delta1.grad = ev.g1
+                if self.delta2 is not None:
+                    self.delta2.grad = ev.g2
             return loss_t
 
         out = []

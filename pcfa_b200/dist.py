@@ -21,14 +21,17 @@ def pack_reduce_unpack(flat: torch.Tensor, loss: torch.Tensor, g1: torch.Tensor,
     """All-reduce (mean) of the gradients and the loss through one preallocated flat buffer.
     Gradients are overwritten in place; the reduced loss is returned as a view of `flat`."""
     n1 = g1.numel()
-    flat[:n1].copy_(g1.reshape(-1))
-    if g2 is not None:
-        flat[n1:n1 + g2.numel()].copy_(g2.reshape(-1))
+    in_place = g1.data_ptr() == flat.data_ptr()          # gradients already are slices of `flat` (DeviceLBFGS layout)
+    if not in_place:
+        flat[:n1].copy_(g1.reshape(-1))
+        if g2 is not None:
+            flat[n1:n1 + g2.numel()].copy_(g2.reshape(-1))
     flat[-1:].copy_(loss.reshape(1))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat)
         flat.div_(dist.get_world_size())
-    g1.reshape(-1).copy_(flat[:n1])
-    if g2 is not None:
-        g2.reshape(-1).copy_(flat[n1:n1 + g2.numel()])
+    if not in_place:
+        g1.reshape(-1).copy_(flat[:n1])
+        if g2 is not None:
+            g2.reshape(-1).copy_(flat[n1:n1 + g2.numel()])
     return flat[-1]
