@@ -36,6 +36,11 @@ def test_status_strings_and_argument_errors():
     assert lib.pcfa_corr_lookup_forward(None, None, None, 1, 8, 8, 4, 4, None) == -1
     assert lib.pcfa_corr_pyramid_forward(None, None, None, None, 0, 1, 8, 8, 8, 4, 0, None) == -1
     assert lib.pcfa_resample2d_forward(None, None, None, 1, 3, 8, 8, 8, 8, 1, 1, None) == -1
+    assert lib.pcfa_instnorm_forward(None, None, None, None, 1, 4, 8, 8, 1e-5, 1, 0, None) == -1
+    assert lib.pcfa_gru_gates_x_forward(None, None, None, None, None, None, None, 128, 128, 10, None) == -1
+    assert lib.pcfa_cat_channels_last(None, None, 2, None, 10, None) == -1
+    assert lib.pcfa_lbfgs_direction(None, None, None, None, None, None, None, None, 10, 100, 0, 0, None) == -1
+    assert lib.pcfa_lbfgs_workspace_bytes() > 0 and lib.pcfa_instnorm_workspace_bytes(2, 64, 220, 512) > 0
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(-1, "x")
 
