@@ -6,8 +6,12 @@ the DataParallel wrapper are accepted, ownutilities.py:105-107), so a user can l
 `raft-sintel.pth` unchanged.  Only the cost-volume operator differs: `corr_block` is injected
 (default: pcfa_b200.corr_block.CorrBlock) — tests inject the oracle to obtain reference flows.
 
-Convolutions, norms and the GRU stay in cuDNN/ATen (library code, not on this project's kernel
-list).  Dead work of the reference's test-mode forward is not executed: the convex-upsampling
+The convolutions stay in cuDNN (library code).  On a GPU the glue around them uses this package's fused
+kernels: instance norm + ReLU in one op, eval-mode batch norm folded into the frozen
+convolution weights, encoders and the RAFT update block in channels-last memory (cuDNN's sm_100 kernels are
+NHWC-only), the GRU's element-wise halves fused, its context-feature share hoisted out of the iteration loop.  CPU
+tensors take the plain nn-module composition, which is what the oracle-injected parity tests run.
+Dead work of the reference's test-mode forward is not executed: the convex-upsampling
 mask head and `upsample_flow` run only for the last iteration, because `test_mode=True` returns
 nothing else (raft.py:141-142) — outputs and gradients are unchanged.
 """
