@@ -94,3 +94,40 @@ def test_universal_reduction_protocol_gloo_world2():
         assert torch.allclose(g1, exp1)
         assert torch.equal(out[0][2], out[1][2])
     assert out[0][3] == [0, 2, 4, 6, 8] and out[1][3] == [1, 3, 5, 7, 9]
+
+
+# ----------------------------------------------------------------------------------- evaluation path (f-3)
+def test_extract_epoch_patchlist_and_repadding(tmp_path):
+    """evaluate_PCFA.py:21-79: discovery of the per-epoch perturbation files and re-padding between the RAFT family
+    (multiples of 8, centred) and the PWCNet/FlowNet2 family (multiples of 64)."""
+    import numpy as np
+    import torch
+    from pcfa_b200.adapter import InputPadder
+    from pcfa_b200.evaluate import convert_perturbationsizes, extract_epoch_patchlist, l2_metrics
+    run = tmp_path / "run"
+    (run / "patches").mkdir(parents=True)
+    for e in range(3):
+        np.save(run / "patches" / ("%05d_delta1_e%d.npy" % (e, e)), np.full((3, 4, 4), e, np.float32))
+        np.save(run / "patches" / ("%05d_delta2_e%d.npy" % (e, e)), np.zeros((3, 4, 4), np.float32))
+    np.save(run / "patches" / "00000_image1.npy", np.zeros(1))                      # ignored
+    epochs, d1, d2 = extract_epoch_patchlist(str(run))
+    assert epochs == 3 and len(d1) == 3 and len(d2) == 3 and d1[2].endswith("00002_delta1_e2.npy")
+    assert extract_epoch_patchlist(d1[0]) == (1, [d1[0]], [])
+    with pytest.raises(ValueError):
+        (tmp_path / "x.txt").write_text("x")
+        extract_epoch_patchlist(str(tmp_path / "x.txt"))
+    # Sintel: RAFT pads 436 -> 440 (2 + 2 rows); PWCNet/FlowNet2 pad 436 -> 448 (6 + 6 rows)
+    H, W = 436, 1024
+    g = torch.Generator().manual_seed(0)
+    delta = torch.rand(3, 440, 1024, generator=g) * 0.01
+    same = convert_perturbationsizes(delta, (H, W), "RAFT", "GMA")
+    assert same is delta
+    for net in ("FlowNet2", "PWCNet"):
+        out = convert_perturbationsizes(delta, (H, W), "RAFT", net)
+        assert tuple(out.shape) == (3, 448, 1024)
+        core = InputPadder((1, 3, H, W), divisor=64).unpad(out)
+        torch.testing.assert_close(core, delta[:, 2:438], rtol=1e-6, atol=1e-9)      # unit-input /255 is undone
+    back = convert_perturbationsizes(convert_perturbationsizes(delta, (H, W), "RAFT", "FlowNet2"), (H, W), "FlowNet2", "RAFT")
+    torch.testing.assert_close(back[:, 2:438], delta[:, 2:438])
+    l1, l2, l12 = l2_metrics(torch.full((3, 2, 2), 0.1), torch.zeros(3, 2, 2))
+    assert l1 == pytest.approx(0.1) and l2 == 0.0 and l12 == pytest.approx(0.1 / 2 ** 0.5)
