@@ -258,7 +258,7 @@ def run_b200(args):
 
     out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN convs with torch's default TF32; cost volume bf16x3-split or fp32 SIMT, fp32 accumulate)",
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensors fp32 end to end; cuDNN convolutions with torch's default TF32; cost-volume build bf16x3 split with fp32 accumulation ~1e-5, its backward TF32 3e-4)",
            "data": "synthetic", "config": config_dict(args, world),
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
