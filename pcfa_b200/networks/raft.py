@@ -47,7 +47,8 @@ def _norm_act(norm: nn.Module, x: torch.Tensor, relu: bool) -> torch.Tensor:
 def _bn_folded(conv: nn.Conv2d, bn: nn.BatchNorm2d):
     """Eval-mode BatchNorm is a per-channel affine map: fold it into the preceding convolution's frozen weights
     (W * s, b * s + t with s = gamma / sqrt(var + eps), t = beta - mean * s).  Cached per module; the key notices
-    in-place updates and re-allocation of any tensor involved."""
+    re-allocation and version-counted in-place updates (load_state_dict, copy_, optimiser steps) of any tensor involved —
+    not writes through `.data`."""
     ts = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
     key = tuple((t.data_ptr(), t._version) for t in ts if t is not None)
     cache = getattr(conv, "_pcfa_bn_fold", None)

@@ -131,3 +131,55 @@ def test_extract_epoch_patchlist_and_repadding(tmp_path):
     torch.testing.assert_close(back[:, 2:438], delta[:, 2:438])
     l1, l2, l12 = l2_metrics(torch.full((3, 2, 2), 0.1), torch.zeros(3, 2, 2))
     assert l1 == pytest.approx(0.1) and l2 == 0.0 and l12 == pytest.approx(0.1 / 2 ** 0.5)
+
+
+# ----------------------------------------------------------------------------------- encoder / GRU weight algebra (f-4)
+def test_bn_fold_and_gru_weight_split_are_exact_algebra():
+    """The frozen-weight rewrites the GPU path relies on, checked on CPU with plain torch ops:
+    eval batch norm folded into the convolution, convz|convr as one convolution, and the context-feature share of
+    the GRU convolutions hoisted out of the loop (conv([h|inp|motion]) = conv_hm([h|motion]) + conv_inp(inp) + b)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from pcfa_b200.networks.raft import SepConvGRU, _bn_folded, _zr_weights
+    torch.manual_seed(0)
+    conv, bn = nn.Conv2d(5, 7, 3, padding=1, stride=2), nn.BatchNorm2d(7)
+    bn.running_mean.uniform_(-1, 1); bn.running_var.uniform_(0.5, 2); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.uniform_(-1, 1)
+    bn.eval()
+    x = torch.randn(2, 5, 9, 11)
+    w, b = _bn_folded(conv, bn)
+    torch.testing.assert_close(F.conv2d(x, w, b, conv.stride, conv.padding), bn(conv(x)), rtol=1e-5, atol=1e-5)
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                                   # in-place update (version counter) invalidates the cache
+    w2, _ = _bn_folded(conv, bn)
+    assert not torch.equal(w, w2)
+
+    gru = SepConvGRU(hidden_dim=8, input_dim=8 + 12).eval()                     # x = [inp (8) | motion (12)]
+    h, inp, motion = torch.randn(1, 8, 6, 7), torch.randn(1, 8, 6, 7), torch.randn(1, 12, 6, 7)
+    wz, bz = _zr_weights(gru.convz1, gru.convr1)
+    hx = torch.cat([h, inp, motion], 1)
+    zr = F.conv2d(hx, wz, bz, 1, gru.convz1.padding)
+    torch.testing.assert_close(zr[:, :8], gru.convz1(hx)); torch.testing.assert_close(zr[:, 8:], gru.convr1(hx))
+    hoist = gru.hoisted(inp)
+    (wzr1, pzr1, wq1, pq1, pad1), (wzr2, pzr2, wq2, pq2, pad2) = hoist
+    hm = torch.cat([h, motion], 1)
+    torch.testing.assert_close(F.conv2d(hm, wzr1, None, 1, pad1) + pzr1, zr, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(F.conv2d(hm, wq1, None, 1, pad1) + pq1, gru.convq1(hx), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(F.conv2d(hm, wzr2, None, 1, pad2) + pzr2,
+                               torch.cat([gru.convz2(hx), gru.convr2(hx)], 1), rtol=1e-5, atol=1e-5)
+    # the whole hoisted step equals the reference composition (models/raft/update.py:33-60) with torch ops
+    def step(h, cz, cr, cq):
+        x = torch.cat([inp, motion], 1)
+        hx = torch.cat([h, x], 1)
+        z, r = torch.sigmoid(cz(hx)), torch.sigmoid(cr(hx))
+        q = torch.tanh(cq(torch.cat([r * h, x], 1)))
+        return (1 - z) * h + z * q
+    ref = step(step(h, gru.convz1, gru.convr1, gru.convq1), gru.convz2, gru.convr2, gru.convq2)
+    def step_x(h, wzr, pzr, wq, pq, pad):
+        zr = F.conv2d(torch.cat([h, motion], 1), wzr, None, 1, pad) + pzr
+        z, r = torch.sigmoid(zr[:, :8]), torch.sigmoid(zr[:, 8:])
+        q = torch.tanh(F.conv2d(torch.cat([r * h, motion], 1), wq, None, 1, pad) + pq)
+        return (1 - z) * h + z * q
+    out = step_x(step_x(h, *hoist[0]), *hoist[1])
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gru(h, torch.cat([inp, motion], 1)), ref, rtol=1e-6, atol=1e-6)   # CPU module path
