@@ -48,11 +48,15 @@ class _InstNormFn(Function):
 
 
 def instance_norm(x: torch.Tensor, eps: float = 1e-5, relu: bool = False) -> torch.Tensor:
-    """relu?(F.instance_norm(x, eps=eps)) for a CUDA fp32 4-D tensor (no affine, no running statistics)."""
+    """relu?(F.instance_norm(x, eps=eps)) for a CUDA 4-D tensor (no affine, no running statistics).  Half-precision
+    inputs (convolution outputs under autocast, GMA's default) are normalised in fp32 and returned in fp32, which is
+    what autocast makes of F.instance_norm as well."""
+    if x.dtype != torch.float32:
+        x = x.float()
     return _InstNormFn.apply(x, eps, relu)
 
 
 def fusable(norm: torch.nn.Module, x: torch.Tensor) -> bool:
     """True when `norm` is a plain nn.InstanceNorm2d that the fused kernel reproduces and x lives on a GPU."""
     return (isinstance(norm, torch.nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats
-            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4)
+            and x.is_cuda and x.dtype in (torch.float32, torch.float16, torch.bfloat16) and x.dim() == 4)
