@@ -69,9 +69,12 @@ def main(argv=None):
     tag = "%s_PCFA_%s_%s" % (args.net, "cd" if args.joint_perturbation else "dd", "u" if args.universal_perturbation else "-")
     folder = None
     if not args.no_save:
-        folder = Path(args.output_folder) / tag / time.strftime("%Y-%m-%d_%H:%M:%S") / "patches"
-        if rank == 0:
-            folder.mkdir(parents=True, exist_ok=True)
+        stamp = [time.strftime("%Y-%m-%d_%H:%M:%S")]
+        if world > 1:                                                # one folder name for all ranks (rank 0's clock)
+            import torch.distributed as dist
+            dist.broadcast_object_list(stamp, src=0)
+        folder = Path(args.output_folder) / tag / stamp[0] / "patches"
+        folder.mkdir(parents=True, exist_ok=True)
     if rank == 0:
         print(args)
         _header(args, mu, folder)
@@ -79,7 +82,8 @@ def main(argv=None):
     t0 = time.time()
     if args.universal_perturbation:
         ua = UniversalAttack(model, args.net, (H, W), device, delta_bound=args.delta_bound, mu=args.mu, target=args.target,
-                             loss=args.loss, joint_perturbation=args.joint_perturbation)
+                             loss=args.loss, joint_perturbation=args.joint_perturbation,
+                             custom_target_path=args.custom_target_path)
         per_rank = max(1, args.batch_size // world)
         n_batches = max(1, n_pairs // (per_rank * world))
         for epoch in range(args.epochs):

@@ -49,7 +49,8 @@ def main(argv=None):
             delta2 = delta1
         else:
             delta2 = convert_perturbationsizes(load_delta(d2_paths[epoch], device), (H, W), args.origin_net, args.net)
-        res = evaluate_perturbation(model, args.net, delta1, delta2, batches(), joint=args.joint_perturbation)
+        res = evaluate_perturbation(model, args.net, delta1, delta2, batches(), joint=args.joint_perturbation,
+                                    boxconstraint=args.boxconstraint)
         l2 = l2_metrics(delta1, delta2)
         print("Finished attacking epoch %d" % epoch)
         print("\tAEE(f_adv, f_init)=%f" % res["aee_adv_pred"])

@@ -43,12 +43,28 @@ def get_target(target_name, flow_pred_init, custom_target_path="", device=None):
     if target_name == 'neg_flow':
         return -flow_pred_init
     if target_name == 'custom':
+        # targets.py:60-80: [2,H,W] flow, cropped or reflect-padded (right / bottom) to the flow's size, repeated over
+        # the batch.  Offline build: the file is a .npy array ([2,H,W], [H,W,2] or [1,2,H,W]) instead of a .flo/.png.
         import numpy as np
+        import torch.nn.functional as F
         t = torch.from_numpy(np.load(custom_target_path).astype("float32")).to(flow_pred_init.device)
-        if t.dim() == 3:
-            t = t[None].expand_as(flow_pred_init)
-        if t.shape != flow_pred_init.shape:
-            raise ValueError("custom target has shape %s, flow has %s" % (tuple(t.shape), tuple(flow_pred_init.shape)))
+        if t.dim() == 4:
+            t = t[0]
+        if t.dim() != 3:
+            raise ValueError("custom target must be a flow field, got shape %s" % (tuple(t.shape),))
+        if t.shape[0] != 2 and t.shape[-1] == 2:
+            t = t.permute(2, 0, 1)
+        Hf, Wf = flow_pred_init.shape[-2:]
+        if Wf < t.shape[-1]:
+            t = t[:, :, :Wf]
+        elif Wf > t.shape[-1]:
+            t = F.pad(t[None], (0, Wf - t.shape[-1]), "reflect")[0]
+        if Hf < t.shape[-2]:
+            t = t[:, :Hf, :]
+        elif Hf > t.shape[-2]:
+            t = F.pad(t[None], (0, 0, 0, Hf - t.shape[-2]), "reflect")[0]
+        if flow_pred_init.dim() == 4:
+            t = t[None].repeat(flow_pred_init.shape[0], 1, 1, 1)
         return t.contiguous()
     raise ValueError("The specified target type '%s' is not defined" % target_name)
 
@@ -255,8 +271,10 @@ class UniversalAttack:
     all-reduces [grad_delta1 | grad_delta2 | loss] (sum, then / world_size)."""
 
     def __init__(self, model, net_name, image_shape, device, *, delta_bound=0.005, mu=-1., target='zero', loss='aee',
-                 joint_perturbation=False, eps_box=1e-7, iters=None, lbfgs_max_iter=10, use_graph=False, lbfgs="device"):
+                 joint_perturbation=False, eps_box=1e-7, iters=None, lbfgs_max_iter=10, use_graph=False, lbfgs="device",
+                 custom_target_path=""):
         self.model, self.net_name, self.device = model, net_name, device
+        self.custom_target_path = custom_target_path
         self.delta_bound, self.target, self.loss = delta_bound, target, loss
         self.mu = resolve_mu(mu, delta_bound, target)
         self.joint, self.eps_box, self.iters, self.use_graph = joint_perturbation, eps_box, iters, use_graph
@@ -304,7 +322,7 @@ class UniversalAttack:
                               joint=self.joint, pad=self.padder.top_left, eps_box=self.eps_box, scale=scale,
                               delta_bound=self.delta_bound, mu=self.mu, loss=self.loss)
         flow_init = self.padder.unpad(fo.predict(zero, None if self.joint else zero)).contiguous().clone()
-        fo.target.copy_(get_target(self.target, flow_init))
+        fo.target.copy_(get_target(self.target, flow_init, self.custom_target_path))
         d1 = self.delta1.detach()
         d2 = None if self.delta2 is None else self.delta2.detach()
         ev = GraphedEvaluate(fo, d1, d2, use_graph=self.use_graph, g1=self.g1, g2=self.g2)

@@ -62,9 +62,14 @@ def l2_metrics(delta1: torch.Tensor, delta2: torch.Tensor):
 
 @torch.no_grad()
 def evaluate_perturbation(model, net_name: str, delta1: torch.Tensor, delta2: torch.Tensor | None, batches, *,
-                          joint: bool, iters=None):
+                          joint: bool, iters=None, boxconstraint: str = "clipping", eps_box: float = 1e-7):
     """batches: iterable of (image1, image2) in [0,255], [b,3,H,W] on the device.  delta2=None or joint=True applies
-    delta1 to both frames.  Returns dict(aee_adv_pred=mean AEE(f_adv, f_init), images=count)."""
+    delta1 to both frames.  Returns dict(aee_adv_pred=mean AEE(f_adv, f_init), images=count).
+
+    boxconstraint="change_of_variables" reproduces the reference's default evaluation (evaluate_PCFA.py:151-154 builds
+    the ScaledInputModel with variable_change=True): image+delta goes through the tanh transform as if it were the
+    w-variable (own_models.py:62-85), for the unperturbed prediction as well.  That composition is forward-only and
+    outside the attack's hot path, so it runs as four element-wise torch ops in front of the network."""
     from .attack import _net_forward, avg_epe
     unit = model_takes_unit_input(net_name)
     fwd = _net_forward(model, net_name, iters)
@@ -81,9 +86,20 @@ def evaluate_perturbation(model, net_name: str, delta1: torch.Tensor, delta2: to
         fo = J.FusedObjective(fwd, image1, image2, torch.zeros(b, 2, H, W, device=image1.device), mode=J.BOX_UNIVERSAL,
                               joint=d2 is None, pad=padder.top_left, eps_box=0.0, scale=1.0 if unit else 255.0,
                               delta_bound=1.0, mu=0.0, loss="aee")
-        zero = torch.zeros_like(d1)
-        flow_init = padder.unpad(fo.predict(zero, None if d2 is None else zero)).contiguous().clone()
-        flow_adv = padder.unpad(fo.predict(d1, d2))
+        if boxconstraint == "change_of_variables":
+            sc = 1.0 if unit else 255.0
+
+            def cov(img, d):
+                x = img if d is None else img + d
+                x = 0.5 / (1.0 - eps_box) * (torch.tanh(x) + (1.0 - eps_box))
+                return (torch.clamp(x, 0.0, 1.0) * sc).contiguous()
+            dd2 = d1 if d2 is None else d2
+            flow_init = padder.unpad(fwd(cov(image1, None), cov(image2, None))).contiguous().clone()
+            flow_adv = padder.unpad(fwd(cov(image1, d1), cov(image2, dd2)))
+        else:
+            zero = torch.zeros_like(d1)
+            flow_init = padder.unpad(fo.predict(zero, None if d2 is None else zero)).contiguous().clone()
+            flow_adv = padder.unpad(fo.predict(d1, d2))
         for i in range(b):
             total += float(avg_epe(flow_adv[i:i + 1], flow_init[i:i + 1]))
         count += b

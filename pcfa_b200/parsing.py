@@ -14,8 +14,9 @@ def create_parser(stage="training", attack_type="pcfa"):
         raise ValueError('This build implements the "pcfa" attack only')
     p = argparse.ArgumentParser(usage='%(prog)s [options (see below)]')
     g = p.add_argument_group(title='network arguments')
-    g.add_argument('--net', default='SpyNet', choices=['RAFT', 'GMA', 'PWCNet', 'SpyNet', 'FlowNet2'],
-                   help="specify the network under attack")
+    # the reference also lists SpyNet (its default): it has no cost volume and is not part of this build
+    g.add_argument('--net', default='RAFT', choices=['RAFT', 'GMA', 'PWCNet', 'FlowNet2'],
+                   help="specify the network under attack (SpyNet is not implemented in this build)")
     g = p.add_argument_group(title="dataset arguments")
     g.add_argument('--dataset', default='Kitti15', choices=['Kitti15', 'Sintel'])
     g.add_argument('--dataset_stage', default='evaluation', choices=['training', 'evaluation'])
