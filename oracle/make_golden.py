@@ -204,6 +204,20 @@ def golden_raft():
                         g_img1=_np(i1.grad), g_img2=_np(i2.grad))
 
 
+def _stub_flownet2_extensions():
+    """FlowNet2's three CUDA-only extension modules → the oracle's operator classes (they cannot execute on CPU)."""
+    sys.path.insert(0, str(REPO))
+    from oracle import torch_ref as TR
+    for pkg, mod, name in (("correlation_package", "correlation", "Correlation"), ("resample2d_package", "resample2d", "Resample2d"),
+                           ("channelnorm_package", "channelnorm", "ChannelNorm")):
+        m = types.ModuleType(f"models.FlowNet.{pkg}.{mod}")
+        setattr(m, name, getattr(TR, name))
+        pk = types.ModuleType(f"models.FlowNet.{pkg}")
+        pk.__path__ = []
+        setattr(pk, mod, m)
+        sys.modules[f"models.FlowNet.{pkg}"], sys.modules[f"models.FlowNet.{pkg}.{mod}"] = pk, m
+
+
 def golden_networks():
     """Reference GMA / PWCNet / FlowNet2 forward (and PWCNet backward) with name-keyed weights.  FlowNet2's three
     CUDA-only extension modules are replaced by the oracle's operator classes (they cannot execute on CPU)."""
@@ -226,14 +240,7 @@ def golden_networks():
     go = torch.randn(flow.shape, generator=torch.Generator().manual_seed(16)) / flow.numel()
     (flow * go).sum().backward()
     blob.update(pwc_flow=_np(flow), pwc_gout=_np(go), pwc_g_img1=_np(a.grad))
-    for pkg, mod, name in (("correlation_package", "correlation", "Correlation"), ("resample2d_package", "resample2d", "Resample2d"),
-                           ("channelnorm_package", "channelnorm", "ChannelNorm")):
-        m = types.ModuleType(f"models.FlowNet.{pkg}.{mod}")
-        setattr(m, name, getattr(TR, name))
-        pk = types.ModuleType(f"models.FlowNet.{pkg}")
-        pk.__path__ = []
-        setattr(pk, mod, m)
-        sys.modules[f"models.FlowNet.{pkg}"], sys.modules[f"models.FlowNet.{pkg}.{mod}"] = pk, m
+    _stub_flownet2_extensions()
     from models.FlowNet.FlowNet2 import FlowNet2
     net = deterministic_state_(FlowNet2(Namespace(fp16=False, rgb_max=255.0), div_flow=20, batchNorm=False), 0, gain=0.7).eval()
     i1, i2 = synthetic_pair(5, 64, 128)
@@ -293,12 +300,240 @@ def golden_attack():
         torch.autograd.set_detect_anomaly(False)
 
 
+# --------------------------------------------------------------------------------------------------------------
+# Round 2: trajectory-pinned closures, the universal attack, full-shape networks
+class _RecordingLBFGS(torch.optim.LBFGS):
+    """torch.optim.LBFGS that records, for chosen closure evaluations (1-based, counted over the whole run), the
+    iterate the closure was evaluated at and the loss / gradient it returned."""
+    WANT = ()
+    LOG = None
+    SAMPLE = 4096
+
+    def step(self, closure):
+        params = self.param_groups[0]["params"]
+
+        def recording():
+            loss = closure()
+            log = _RecordingLBFGS.LOG
+            log["n"] += 1
+            if log["n"] in _RecordingLBFGS.WANT:
+                k = log["n"]
+                flat_g = torch.cat([p.grad.reshape(-1) for p in params])
+                idx = torch.linspace(0, flat_g.numel() - 1, _RecordingLBFGS.SAMPLE).long()
+                log["rec"][k] = dict(iterate=[_np(p) for p in params], loss=float(loss),
+                                     gnorm=[float(p.grad.norm()) for p in params],
+                                     gsample=_np(flat_g[idx]), gidx=idx.numpy().astype(np.int64))
+            return loss
+        return super().step(recording)
+
+
+def _fake_loader(cfg, gain_box):
+    from helper_functions.own_models import ScaledInputModel
+    from models.raft.raft import RAFT
+    from pcfa_b200.networks.weights import deterministic_state_
+
+    def fake_import_and_load(net='RAFT', make_unit_input=False, variable_change=False, device=None,
+                             make_scaled_input_model=False, **kw):
+        if make_scaled_input_model:                      # ownutilities.py:86-88
+            kw.pop("device", None)
+            return ScaledInputModel(net, make_unit_input=make_unit_input, variable_change=variable_change, **kw)
+        m = torch.nn.DataParallel(RAFT(dict(cfg)))            # ownutilities.py:105
+        deterministic_state_(m, seed=0, strip_prefix="module.", gain=gain_box[0])
+        return m
+    return fake_import_and_load
+
+
+def golden_trajectory():
+    """The reference's pcfa_attack (disjoint, change_of_variables) with a recording optimiser: the iterates (w1, w2)
+    the reference evaluated its closure at — closures 1, 11, 22, 33 = first closure of outer steps 1-3 and the last
+    one of step 3 — with the loss, gradient norms and a 4096-element gradient sample the REFERENCE obtained there.
+    A GPU test re-evaluates the fused closure at exactly these iterates (attack_PCFA.py:175-189), which pins every
+    step of the attack without depending on the chaotic L-BFGS trajectory."""
+    import tempfile
+    import attack_PCFA
+    from helper_functions import ownutilities, parsing_file
+    from helper_functions.own_models import ScaledInputModel
+    sys.path.insert(0, str(REPO))
+    from pcfa_b200.networks.weights import synthetic_pair
+    cfg = json.load(open(REF / "models/_config/raft_config.json"))
+    GAIN = [1.0]
+    real, real_opt = ownutilities.import_and_load, attack_PCFA.optim.LBFGS
+    ownutilities.import_and_load = _fake_loader(cfg, GAIN)
+    attack_PCFA.optim.LBFGS = _RecordingLBFGS
+    blob = {}
+    try:
+        for tag, gain in (("g05", 0.5), ("g10", 1.0)):
+            GAIN[0] = gain
+            _RecordingLBFGS.WANT = (1, 11, 22, 33)
+            _RecordingLBFGS.LOG = dict(n=0, rec={})
+            args = parsing_file.create_parser('training', 'pcfa').parse_args(
+                ["--net", "RAFT", "--steps", "3", "--no_save", "--delta_bound", "0.005"])
+            model = ScaledInputModel("RAFT", make_unit_input=True, variable_change=True, eps_box=1e-7).eval()
+            for p in model.parameters():
+                p.requires_grad = False
+            i1, i2 = synthetic_pair(0, 128, 160)
+            with tempfile.TemporaryDirectory() as tmp:
+                attack_PCFA.pcfa_attack(model, i1, i2, torch.zeros(1, 2, 128, 160), 0, tmp, 1e-7, torch.device("cpu"),
+                                        False, 2500. / 0.005, args)
+            rec = _RecordingLBFGS.LOG["rec"]
+            print("trajectory", tag, "closures seen:", _RecordingLBFGS.LOG["n"], "recorded:", sorted(rec))
+            for k, r in rec.items():
+                blob[f"{tag}_c{k}_w1"], blob[f"{tag}_c{k}_w2"] = r["iterate"]
+                blob[f"{tag}_c{k}_loss"] = np.float64(r["loss"])
+                blob[f"{tag}_c{k}_gnorm"] = np.asarray(r["gnorm"], np.float64)
+                blob[f"{tag}_c{k}_gsample"] = r["gsample"]
+                blob[f"{tag}_c{k}_gidx"] = r["gidx"]
+            blob[f"{tag}_closures"] = np.asarray(sorted(rec), np.int64)
+    finally:
+        ownutilities.import_and_load, attack_PCFA.optim.LBFGS = real, real_opt
+        torch.autograd.set_detect_anomaly(False)
+    np.savez_compressed(OUT / "attack_trajectory.npz", **blob)
+
+
+def golden_universal():
+    """The reference's attack_l2_universal (attack_PCFA.py:297-566) on CPU: RAFT (damped name-keyed weights), one batch
+    of two synthetic 128x160 pairs, 2 outer L-BFGS steps, one epoch; joint and per-frame perturbations.  The data
+    loader, the model loader and the mlflow / image-file logging are shimmed; the optimisation code is untouched."""
+    import contextlib
+    import attack_PCFA
+    from helper_functions import logging as rlog
+    from helper_functions import ownutilities, parsing_file
+    sys.path.insert(0, str(REPO))
+    from pcfa_b200.networks.weights import synthetic_pair
+    cfg = json.load(open(REF / "models/_config/raft_config.json"))
+    GAIN = [0.5]
+    pairs = [synthetic_pair(i, 128, 160) for i in range(2)]
+    batch = (torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs]), torch.zeros(2, 2, 128, 160), None)
+    saved = dict(import_and_load=ownutilities.import_and_load, prepare_dataloader=ownutilities.prepare_dataloader,
+                 opt=attack_PCFA.optim.LBFGS, setup=rlog.mlflow_experimental_setup, save_tensor=rlog.save_tensor,
+                 save_image=rlog.save_image, save_flow=rlog.save_flow, adv=rlog.calc_metrics_adv,
+                 start_run=getattr(attack_PCFA.mlflow, "start_run", None), sub=rlog.create_subfolder)
+    out = {}
+    blob = {}
+    try:
+        ownutilities.import_and_load = _fake_loader(cfg, GAIN)
+        ownutilities.prepare_dataloader = lambda *a, **k: ([tuple(t.clone() if t is not None else 0 for t in batch)], False)
+        attack_PCFA.optim.LBFGS = _RecordingLBFGS
+        rlog.mlflow_experimental_setup = lambda *a, **k: (0, "/tmp/pcfa_golden_universal", "run")
+        rlog.create_subfolder = lambda *a, **k: "/tmp/pcfa_golden_universal"
+        rlog.save_image = lambda *a, **k: None
+        rlog.save_flow = lambda *a, **k: None
+        attack_PCFA.mlflow.start_run = lambda *a, **k: contextlib.nullcontext()
+        for tag, extra in (("joint", ["--joint_perturbation"]), ("perframe", [])):
+            stats, tensors = [], {}
+            rlog.calc_metrics_adv = (lambda f: (lambda *a: (stats.append(tuple(float(v) for v in f(*a))) or stats[-1])))(saved["adv"])
+            rlog.save_tensor = lambda t, name, *a, **k: tensors.__setitem__(name, _np(t))
+            _RecordingLBFGS.WANT = (1, 11, 12)
+            _RecordingLBFGS.LOG = dict(n=0, rec={})
+            args = parsing_file.create_parser('training', 'pcfa').parse_args(
+                ["--net", "RAFT", "--steps", "2", "--epochs", "1", "--batch_size", "2", "--delta_bound", "0.005",
+                 "--universal_perturbation", "--boxconstraint", "clipping", "--dataset", "Sintel"] + extra)
+            attack_PCFA.attack_l2_universal(args)
+            rec = _RecordingLBFGS.LOG["rec"]
+            print("universal", tag, stats, "closures:", _RecordingLBFGS.LOG["n"])
+            out[tag] = dict(steps=[dict(aee_adv_tgt=a, aee_adv_pred=b) for a, b in stats], closures=_RecordingLBFGS.LOG["n"],
+                            l2_delta1=float(np.sqrt(np.mean(tensors["delta1_e0"] ** 2))))
+            blob[f"{tag}_delta1"] = tensors["delta1_e0"]
+            if "delta2_e0" in tensors:
+                blob[f"{tag}_delta2"] = tensors["delta2_e0"]
+            for k, r in rec.items():
+                for j, it in enumerate(r["iterate"]):
+                    blob[f"{tag}_c{k}_d{j + 1}"] = it
+                blob[f"{tag}_c{k}_loss"] = np.float64(r["loss"])
+                blob[f"{tag}_c{k}_gnorm"] = np.asarray(r["gnorm"], np.float64)
+                blob[f"{tag}_c{k}_gsample"], blob[f"{tag}_c{k}_gidx"] = r["gsample"], r["gidx"]
+            blob[f"{tag}_closures"] = np.asarray(sorted(rec), np.int64)
+    finally:
+        ownutilities.import_and_load, ownutilities.prepare_dataloader = saved["import_and_load"], saved["prepare_dataloader"]
+        attack_PCFA.optim.LBFGS = saved["opt"]
+        rlog.mlflow_experimental_setup, rlog.save_tensor, rlog.save_image = saved["setup"], saved["save_tensor"], saved["save_image"]
+        rlog.save_flow, rlog.calc_metrics_adv, rlog.create_subfolder = saved["save_flow"], saved["adv"], saved["sub"]
+        torch.autograd.set_detect_anomaly(False)
+    (OUT / "attack_universal.json").write_text(json.dumps(out, indent=1))
+    np.savez_compressed(OUT / "attack_universal.npz", **blob)
+
+
+def golden_fullshape():
+    """One reference forward per network at the BASELINE shapes (Sintel 436x1024 for RAFT / GMA, KITTI 375x1242 for
+    PWCNet / FlowNet2) with name-keyed weights, through the reference's own preprocess_img → compute_flow →
+    postprocess_flow (ownutilities.py:241-345); the un-padded flows are stored sub-sampled (every 8th pixel) to keep
+    the file small.  RAFT additionally at the damped weight set, where the 12-step recurrence is well conditioned."""
+    from argparse import Namespace
+    from helper_functions import ownutilities as U
+    sys.path.insert(0, str(REPO))
+    from pcfa_b200.networks.weights import deterministic_state_, synthetic_pair
+    blob = {}
+
+    def run(net, name, idx, H, W):
+        i1, i2 = synthetic_pair(idx, H, W)
+        padder, (a, b) = U.preprocess_img(name, i1, i2)
+        with torch.no_grad():
+            flow = U.compute_flow(net, name, a, b, test_mode=True)
+            [flow] = U.postprocess_flow(name, padder, flow)
+        assert flow.shape[-2:] == (H, W), flow.shape
+        return _np(flow[:, :, ::8, ::8])
+    from models.raft.raft import RAFT
+    cfg = json.load(open(REF / "models/_config/raft_config.json"))
+    for tag, gain in (("raft_g10", 1.0), ("raft_g05", 0.5)):
+        blob[tag] = run(deterministic_state_(RAFT(dict(cfg)), seed=0, gain=gain).eval(), "RAFT", 0, 436, 1024)
+        print(tag, blob[tag].shape, float(np.abs(blob[tag]).mean()))
+    from models.gma.network import RAFTGMA
+    cfg = json.load(open(REF / "models/_config/gma_config.json"))
+    blob["gma_g05"] = run(deterministic_state_(RAFTGMA(Namespace(**cfg)), 0, gain=0.5).eval(), "GMA", 3, 436, 1024)
+    print("gma", float(np.abs(blob["gma_g05"]).mean()))
+    from models.PWCNet.PWCNet import PWCDCNet
+    blob["pwc_g10"] = run(deterministic_state_(PWCDCNet(), 0).eval(), "PWCNet", 4, 375, 1242)
+    print("pwc", blob["pwc_g10"].shape, float(np.abs(blob["pwc_g10"]).mean()))
+    _stub_flownet2_extensions()
+    from models.FlowNet.FlowNet2 import FlowNet2
+    net = deterministic_state_(FlowNet2(Namespace(fp16=False, rgb_max=255.0), div_flow=20, batchNorm=False), 0, gain=0.7).eval()
+    blob["fn2_g07"] = run(net, "FlowNet2", 5, 375, 1242)
+    print("fn2", blob["fn2_g07"].shape, float(np.abs(blob["fn2_g07"]).mean()))
+    np.savez_compressed(OUT / "networks_fullshape.npz", **blob)
+
+
+def golden_evaluate():
+    """evaluate_PCFA.py:21-79 executed in place: convert_perturbationsizes between the two padding families (and the
+    unit-input rescaling) on a small 52x70 'dataset' shape, and extract_epoch_patchlist on a folder laid out the way
+    attack_PCFA.py --universal_perturbation writes it."""
+    import tempfile
+    import evaluate_PCFA as E
+    g = torch.Generator().manual_seed(21)
+    H, W = 52, 70
+    image = torch.rand(1, 3, H, W, generator=g) * 255.0
+    blob = {"hw": np.asarray([H, W])}
+    cases = [("RAFT", "PWCNet"), ("PWCNet", "RAFT"), ("GMA", "FlowNet2"), ("FlowNet2", "GMA"), ("RAFT", "GMA"), ("PWCNet", "FlowNet2")]
+    for tr, ev in cases:
+        from helper_functions import ownutilities as U
+        _, (padded,) = U.preprocess_img(tr, image.clone())
+        delta = 0.01 * torch.randn(padded.shape[1:], generator=g)
+        out = E.convert_perturbationsizes(delta, image, tr, ev, "Sintel")
+        blob[f"{tr}_{ev}_delta"] = _np(delta)
+        blob[f"{tr}_{ev}_out"] = _np(out)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "patches"))
+        names = ["00003_delta1_e0.npy", "00007_delta1_e1.npy", "00011_delta1_e2.npy", "00003_delta2_e0.npy", "00007_delta2_e1.npy",
+                 "00011_delta2_e2.npy", "00002_delta1_b2.npy", "00000_image1_e0.npy"]
+        for n in names:
+            np.save(os.path.join(tmp, "patches", n), np.zeros(1, np.float32))
+        epochs, d1, d2 = E.extract_epoch_patchlist(tmp)
+        blob["patch_names"] = np.frombuffer(json.dumps(names).encode(), dtype=np.uint8)
+        blob["patch_result"] = np.frombuffer(json.dumps(dict(epochs=int(epochs), d1=[os.path.basename(x) for x in d1],
+                                                              d2=[os.path.basename(x) for x in d2])).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT / "evaluate.npz", **blob)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     _shim_reference()
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    for fn in (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft, golden_networks, golden_attack):
+    fns = (golden_corrblock, golden_scs, golden_objective, golden_pwc_warp, golden_raft, golden_networks, golden_attack,
+           golden_trajectory, golden_universal, golden_fullshape, golden_evaluate)
+    only = set(sys.argv[1:])                 # python -m oracle.make_golden [golden_x ...] regenerates a subset
+    for fn in fns:
+        if only and fn.__name__ not in only:
+            continue
         fn()
         print("wrote", fn.__name__)
 

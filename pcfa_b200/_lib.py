@@ -5,6 +5,7 @@ library is missing or a tensor is not a CUDA tensor the call raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
@@ -99,7 +100,23 @@ def load():
     global _raw
     _raw = lib
     _lib = _LibProxy()
+    apply_determinism_from_env()
     return _lib
+
+
+def deterministic() -> bool:
+    return os.environ.get("PCFA_DETERMINISTIC", "0") not in ("", "0")
+
+
+def apply_determinism_from_env():
+    """PCFA_DETERMINISTIC=1 (read once, when the library is loaded): bit-reproducible closures.  The library side cuts the
+    cost-volume backward's work shares at unit boundaries (one reduce-add per output element, csrc/corr_allpairs_bwd_tc.cu);
+    this side pins cuDNN to deterministic algorithms without autotuning.  The lookup scatters are already deterministic
+    (unique addresses per launch, launches stream-ordered); the warp / resample2d image gradients (PWCNet, FlowNet2) still
+    use floating-point RED.ADD and are NOT covered."""
+    if deterministic():
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
 
 
 class _LibProxy:

@@ -684,10 +684,21 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     const int sms = tc_num_sms();
     const int group = two_cta ? 4 : 2;                  // row blocks per work unit
     static const int env_pdl = [] { const char* e = getenv("PCFA_BWD_PDL"); return e ? atoi(e) : 1; }();
+    // PCFA_DETERMINISTIC=1: shares are cut at unit boundaries only (the share count is a divisor of the unit count), so
+    // every output element receives exactly ONE reduce-add into its zeroed target and the result is bit-reproducible;
+    // the default split-K shares finish partial sums with RED.ADD in arrival order (fp32 addition order varies).
+    static const int env_det = [] { const char* e = getenv("PCFA_DETERMINISTIC"); return e ? atoi(e) : 0; }();
+    auto det_shares = [&](const BwParams& P, long long cap) -> long long {
+        const long long units = P.work_total / P.chunks_total;
+        long long n = units < cap ? units : cap;
+        while (n > 1 && units % n != 0) --n;
+        return n < 1 ? 1 : n;
+    };
     auto launch = [&](const BwMaps& maps, const BwParams& P) -> int {
         if (two_cta) {
             long long clusters = sms / 2;
             if (clusters > P.work_total) clusters = P.work_total;
+            if (env_det) clusters = det_shares(P, sms / 2);
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(BW_THREADS);
             cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
@@ -697,7 +708,7 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
             cfg.attrs = at; cfg.numAttrs = (P.pass == 2 && env_pdl) ? 1 : 0;      // pass II may overlap pass I's tail
             PCFA_CUDA_TRY(cudaLaunchKernelEx(&cfg, corr_pyramid_bwd_tc2_kernel, maps, P));
         } else {
-            const int grid = (int)(P.work_total < sms ? P.work_total : sms);
+            const int grid = env_det ? (int)det_shares(P, sms) : (int)(P.work_total < sms ? P.work_total : sms);
             corr_pyramid_bwd_tc_kernel<<<grid, BW_THREADS, smem, s>>>(maps, P);
         }
         return after_launch();

@@ -183,3 +183,30 @@ def test_bn_fold_and_gru_weight_split_are_exact_algebra():
     out = step_x(step_x(h, *hoist[0]), *hoist[1])
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(gru(h, torch.cat([inp, motion], 1)), ref, rtol=1e-6, atol=1e-6)   # CPU module path
+
+
+def test_evaluate_helpers_match_reference_outputs(golden, tmp_path):
+    """f-3: convert_perturbationsizes and extract_epoch_patchlist against the outputs of the reference's own functions
+    (evaluate_PCFA.py:21-79, executed in place by oracle/make_golden.py::golden_evaluate): re-padding between the
+    RAFT/GMA (multiples of 8, centred) and PWCNet/FlowNet2 (multiples of 64) families incl. the x255 of unit-input
+    networks, and epoch / file discovery in a folder written by attack_PCFA.py --universal_perturbation."""
+    import json
+    from pcfa_b200.evaluate import convert_perturbationsizes, extract_epoch_patchlist
+    z = golden("evaluate")
+    H, W = (int(v) for v in z["hw"])
+    for key in [k for k in z.files if k.endswith("_delta")]:
+        tr, ev = key.split("_")[:2]
+        delta = torch.from_numpy(z[key])
+        want = z[f"{tr}_{ev}_out"]
+        got = convert_perturbationsizes(delta, (H, W), tr, ev).numpy()
+        assert got.shape == want.shape[-3:], (key, got.shape, want.shape)     # the reference keeps a leading batch dim of 1
+        np.testing.assert_array_equal(got, want.reshape(got.shape), err_msg=key)   # padding + exact scaling: bit-exact
+    names = json.loads(bytes(z["patch_names"]).decode())
+    (tmp_path / "patches").mkdir()
+    for n in names:
+        np.save(tmp_path / "patches" / n, np.zeros(1, np.float32))
+    want = json.loads(bytes(z["patch_result"]).decode())
+    epochs, d1, d2 = extract_epoch_patchlist(str(tmp_path))
+    import os
+    assert epochs == want["epochs"]
+    assert [os.path.basename(p) for p in d1] == want["d1"] and [os.path.basename(p) for p in d2] == want["d2"]
