@@ -42,13 +42,13 @@ def _rel_l2(a, b):
 
 
 # ------------------------------------------------------------------ (a) closures along the reference trajectory
-@pytest.mark.parametrize("tag,gain,grad_rel,grad_cos", [("g05", 0.5, 1e-2, 0.999), ("g10", 1.0, 1.5e-1, 0.99)])
+@pytest.mark.parametrize("tag,gain,grad_rel,grad_cos", [("g05", 0.5, 1e-2, 0.999), ("g10", 1.0, 2e-2, 0.999)])
 def test_closure_parity_along_reference_trajectory(golden, fp32_convs, tag, gain, grad_rel, grad_cos):
     """attack_PCFA.py:175-189 evaluated at the iterates the reference's L-BFGS visited (closures 1, 11, 22 = start and
     end of outer step 1, end of outer step 2): loss at rtol 1e-3, gradient against the reference's 4096-element sample.
     g05 = damped, trained-like weights (flows of a few px): the 1e-2 gradient bar.  g10 = undamped random weights
     (flows ~100 px): RAFT's 12-step recurrence amplifies 1e-6 forward differences ~10x per two iterations in the
-    gradient, so only the direction (cosine) and a 15 % norm band are asserted there; the loss bar is the same."""
+    gradient, so the gradient bar there is 2e-2 (measured 4e-3 .. 1.0e-2); the loss bar is the same."""
     from pcfa_b200 import objective as J
     from pcfa_b200.adapter import build_network, preprocess_img
     from pcfa_b200.networks.weights import synthetic_pair
@@ -157,11 +157,11 @@ def test_networks_at_baseline_shapes_match_reference_flows(golden, fp32_convs, n
     got = flow[:, :, ::8, ::8].float().cpu().numpy()
     if key == "raft_g10":
         # undamped random weights at full size: flows of ~100 px through a 12-step recurrence; cuDNN-vs-CPU convolution
-        # rounding is amplified, so the bar is rel-L2 + 99th-percentile instead of every element
+        # rounding is amplified at isolated pixels, so the bar is rel-L2 + 99th-percentile at 1e-3 instead of every element
         rel = _rel_l2(got, z[key])
         err = np.abs(got - z[key]) / (np.abs(z[key]) + 1e-2 * np.sqrt(np.mean(z[key] ** 2)))
         print("raft_g10 rel-L2 %.2e  p99 rel err %.2e" % (rel, np.quantile(err, 0.99)))
-        assert rel < 5e-3 and np.quantile(err, 0.99) < 2e-2
+        assert rel < 1e-4 and np.quantile(err, 0.99) < 1e-3            # measured 5.7e-6 / 2.1e-4
         return
     assert_close(got, z[key], rtol=1e-3, atol_rms=2e-3, what=f"{name} flow at {shape}")
 
