@@ -327,6 +327,21 @@ int pcfa_gru_blend_x_backward(const float* z, const float* q, const float* h, co
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,
                            pcfa_stream_t stream);
 
+/* --------------------------------------------------------------------------- convex up-sampling
+ * RAFT.upsample_flow (models/raft/raft.py:72-83; GMA: models/gma/network.py:59-70): softmax over the 9 taps of the
+ * mask head's 576 channels, convex combination of the 3x3 neighbourhood of 8*flow, pixel-shuffle to [N,2,8H,8W].
+ *   flow        [N,2,H,W]    fp32 NCHW
+ *   mask_cl     [N,H,W,576]  fp32, the mask head's output in torch.channels_last memory; channel = k*64 + i*8 + j
+ *   mask_scale  multiplies the mask before the softmax (0.25 in models/raft/update.py:135) and its gradient
+ *   up          [N,2,8H,8W]  fp32 NCHW
+ * backward: grad_mask_cl has mask_cl's layout; workspace >= pcfa_convex_upsample_workspace_bytes(N,H,W).  No atomics. */
+int64_t pcfa_convex_upsample_workspace_bytes(int N, int H, int W);
+int pcfa_convex_upsample_forward(const float* flow, const float* mask_cl, float* up, int N, int H, int W, float mask_scale,
+                                 pcfa_stream_t stream);
+int pcfa_convex_upsample_backward(const float* flow, const float* mask_cl, const float* grad_up, float* grad_flow,
+                                  float* grad_mask_cl, void* workspace, int64_t workspace_bytes, int N, int H, int W,
+                                  float mask_scale, pcfa_stream_t stream);
+
 /* --------------------------------------------------------------------------- on-device L-BFGS
  * The vector algebra of torch.optim.LBFGS.step (torch/optim/lbfgs.py; the reference's optimiser, attack_PCFA.py:97,114)
  * without its ~4*history ATen launches per iteration.  History: ring buffers S, Y of [history_capacity][n] floats.

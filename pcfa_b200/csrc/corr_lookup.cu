@@ -9,6 +9,7 @@
 // store a full 128-byte line of out[b, ch, q0:q0+32].
 // HBM-bound gather: algorithmic bytes per query per level = (2r+2)^2*4 read + (2r+1)^2*4 written.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pcfa {
 
@@ -195,6 +196,230 @@ corr_lookup_bwd_kernel(const float* __restrict__ gout, const float* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channels-last lookups, second generation (the variants the RAFT closure launches 12x forward + 12x backward).
+//
+// ncu of the first generation at 1x55x128 (profiles/ncu_corr_kernels_r1.txt): 5.4 M warp instructions (190 per
+// (query, level) task) = 60 % issue utilisation while active, 4 dependent DRAM round trips per warp (its four queries
+// are gathered one after the other) and a CTA-wide barrier between gather and output; 0.74 waves, so every CTA's
+// latency chain is the kernel's duration (12-14 us for 20 MB).  Here a WARP owns a (query, level) task end to end:
+//   * no CTA barrier (a warp consumes only what it staged itself, __syncwarp);
+//   * LK_TPW tasks per warp with all of their loads issued before the first use (12 gathers / 9 gradient loads in
+//     flight per lane) and 1174 CTAs x 8 warps = ONE wave at 8 CTAs per SM for B = 1;
+//   * per-lane cell -> (row, col) maps, tap offsets and validity are task-independent and computed once; footprints
+//     that lie completely inside the level (the common case) skip the per-cell bounds tests;
+//   * the footprint loads / gradient REDs carry an L2 evict_last policy: successive GRU iterations look up almost the
+//     same 10x10 footprints (the flow changes by a fraction of a cell), 11 MB per launch, which then survive in the
+//     126 MB L2 between iterations while the update block's activations stream past with normal priority.
+constexpr int LK_WARPS = 8;      // warps per CTA
+constexpr int LK_TPW = 5;        // consecutive queries per warp (at one level)
+constexpr int LK_MIN_CTAS = 5;   // 704 CTAs at 1x55x128 = one wave at 5 CTAs per SM (<= 51 registers)
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_policy(const float* p, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_add_policy(float* p, float v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
+// A warp owns LK_TPW consecutive queries at ONE level, so everything that depends on the level (width, per-lane cell
+// offsets, scale) is set up once per warp; warp g of sample b handles level g % levels of query group g / levels.
+struct LkWarp { int l, q0, nq, Hl, Wl, plane; float scale; int64_t lvl_off; };
+
+template <int LV>
+__device__ __forceinline__ LkWarp lk_warp(int gw, int b, int N, const PyramidLayout& L) {
+    LkWarp w;
+    const int levels = LV ? LV : L.levels;
+    const int qg = LV == 4 ? (gw >> 2) : gw / levels;
+    w.l = gw - qg * levels;
+    w.q0 = qg * LK_TPW;
+    w.nq = min(LK_TPW, N - w.q0);                         // <= 0: nothing to do
+    w.Hl = L.h[w.l]; w.Wl = L.w[w.l];
+    w.plane = w.Hl * w.Wl;
+    w.scale = __int_as_float((127 - w.l) << 23);          // 2^-l exactly: centroid_lvl = coords / 2**i (corr.py:41)
+    w.lvl_off = L.off[w.l] + (int64_t)(b * N + w.q0) * w.plane;
+    return w;
+}
+
+struct LkGeom { int o; float fx, fy; bool interior; int iy0, ix0; };
+
+template <int R>
+__device__ __forceinline__ LkGeom lk_geom(float cx, float cy, const LkWarp& w) {
+    constexpr int F = 2 * R + 2;
+    const float sx = cx * w.scale, sy = cy * w.scale;
+    const float flx = floorf(sx), fly = floorf(sy);
+    LkGeom g;
+    g.ix0 = (int)fminf(fmaxf(flx, -1.0e6f), 1.0e6f) - R;  // same clamp as lookup_geom
+    g.iy0 = (int)fminf(fmaxf(fly, -1.0e6f), 1.0e6f) - R;
+    g.fx = sx - flx; g.fy = sy - fly;
+    g.o = g.iy0 * w.Wl + g.ix0;
+    g.interior = g.iy0 >= 0 && g.ix0 >= 0 && g.iy0 + F <= w.Hl && g.ix0 + F <= w.Wl;
+    return g;
+}
+
+// grid: (ceil(ceil(N/LK_TPW)*levels / LK_WARPS), B); out is [B][N][levels*(2R+1)^2].
+// Addressing: one 64-bit base per array and 32-bit element offsets (a single IMAD.WIDE per access).
+template <int R, int LV>
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_CTAS)
+corr_lookup_fwd_cl2_kernel(const float* __restrict__ pyramid, const float* __restrict__ coords, float* __restrict__ out,
+                           const PyramidLayout L, int N, int hint) {
+    constexpr int D = 2 * R + 1, F = D + 1, FP = F * F, NCH = D * D;
+    constexpr int NLD = (FP + 31) / 32, NOUT = (NCH + 31) / 32;
+    __shared__ float S[LK_WARPS][LK_TPW][FP + 2];           // [FP], [FP+1] = fx, fy of the task
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+    const int CT = (LV ? LV : L.levels) * NCH;
+    const LkWarp w = lk_warp<LV>(blockIdx.x * LK_WARPS + warp, b, N, L);
+    if (w.nq <= 0) return;
+    const uint64_t pol = hint ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const float* lvl = pyramid + w.lvl_off;
+    const float* cxp = coords + ((int64_t)b * 2 * N + w.q0);
+
+    int off[NLD];                                  // per-lane element offset of cell lane+32i inside a footprint
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int cell = lane + 32 * i, r_ = cell / F;
+        off[i] = r_ * w.Wl + (cell - r_ * F);
+    }
+    float cx[LK_TPW], cy[LK_TPW];
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j) {
+        const int jj = min(j, w.nq - 1);
+        cx[j] = cxp[jj];
+        cy[j] = cxp[N + jj];
+    }
+    float v[LK_TPW][NLD];
+    bool inside[LK_TPW];
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j) {
+        const LkGeom g = lk_geom<R>(cx[j], cy[j], w);
+        if (lane == 0) { S[warp][j][FP] = g.fx; S[warp][j][FP + 1] = g.fy; }
+        const int e = min(j, w.nq - 1) * w.plane + g.o;
+        inside[j] = g.interior;
+        if (g.interior) {                          // warp-uniform: footprint inside the level (the common case)
+#pragma unroll
+            for (int i = 0; i < NLD; ++i)
+                v[j][i] = (32 * i + 31 < FP || lane + 32 * i < FP) ? ldg_policy(lvl + (e + off[i]), pol) : 0.f;
+        } else {                                   // rare: bounds-checked, staged directly
+#pragma unroll 1
+            for (int cell = lane; cell < FP; cell += 32) {
+                const int r_ = cell / F, c_ = cell - r_ * F;
+                const bool ok = (unsigned)(g.iy0 + r_) < (unsigned)w.Hl && (unsigned)(g.ix0 + c_) < (unsigned)w.Wl;
+                S[warp][j][cell] = ok ? ldg_policy(lvl + (e + r_ * w.Wl + c_), pol) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) v[j][i] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j)
+        if (inside[j]) {
+#pragma unroll
+            for (int i = 0; i < NLD; ++i)
+                if (32 * i + 31 < FP || lane + 32 * i < FP) S[warp][j][lane + 32 * i] = v[j][i];
+        }
+    __syncwarp();
+
+    int toff[NOUT];                                // output channel -> top-left cell of its 2x2 taps
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) {
+        const int ch = lane + 32 * i;
+        const int a = ch / D, bb = ch - a * D;     // a shifts x, bb shifts y (corr.py:37-43)
+        toff[i] = ch < NCH ? bb * F + a : 0;
+    }
+    float* o = out + ((int64_t)(b * N + w.q0) * CT + (w.l * NCH + lane));
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j) {
+        if (j >= w.nq) break;                      // warp-uniform
+        const float* Sq = S[warp][j];
+        const float fx = Sq[FP], fy = Sq[FP + 1];
+        const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) {
+            if (32 * i + 31 < NCH || lane + 32 * i < NCH) {
+                const float* p = Sq + toff[i];
+                o[j * CT + 32 * i] = w00 * p[0] + w01 * p[1] + w10 * p[F] + w11 * p[F + 1];
+            }
+        }
+    }
+}
+
+// grid as above; gout is [B][N][levels*(2R+1)^2].  Every (q, l, cell) address is touched by one lane of one warp per
+// launch (race-free); RED because successive lookups accumulate into the same buffer in stream order.
+template <int R, int LV>
+__global__ void __launch_bounds__(LK_WARPS * 32, LK_MIN_CTAS)
+corr_lookup_bwd_cl2_kernel(const float* __restrict__ gout, const float* __restrict__ coords, float* __restrict__ gpyr,
+                           const PyramidLayout L, int N, int hint) {
+    constexpr int D = 2 * R + 1, F = D + 1, FP = F * F, NCH = D * D;
+    constexpr int NLD = (FP + 31) / 32, NOUT = (NCH + 31) / 32;
+    constexpr int ZERO = NCH;                      // G[..][ZERO] == 0: target of taps that do not exist
+    __shared__ float G[LK_WARPS][LK_TPW][NCH + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+    const int CT = (LV ? LV : L.levels) * NCH;
+    const LkWarp w = lk_warp<LV>(blockIdx.x * LK_WARPS + warp, b, N, L);
+    if (w.nq <= 0) return;
+    const uint64_t pol = hint ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const float* cxp = coords + ((int64_t)b * 2 * N + w.q0);
+    const float* gi = gout + ((int64_t)(b * N + w.q0) * CT + (w.l * NCH + lane));
+    float* lvl = gpyr + w.lvl_off;
+
+    float cx[LK_TPW], cy[LK_TPW];
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j) {
+        const int jj = min(j, w.nq - 1);
+        cx[j] = cxp[jj];
+        cy[j] = cxp[N + jj];
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i)
+            if (32 * i + 31 < NCH || lane + 32 * i < NCH) G[warp][j][lane + 32 * i] = __ldg(gi + (jj * CT + 32 * i));
+        if (lane == 0) G[warp][j][ZERO] = 0.f;
+    }
+    // cell (rr, cc) receives tap (a=cc, b=rr)*w00 + (cc-1, rr)*w01 + (cc, rr-1)*w10 + (cc-1, rr-1)*w11; tap (a, b) is channel a*D + b
+    int rr[NLD], cc[NLD], off[NLD], i00[NLD], i01[NLD], i10[NLD], i11[NLD];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int cell = lane + 32 * i;
+        rr[i] = cell / F; cc[i] = cell - rr[i] * F;
+        off[i] = rr[i] * w.Wl + cc[i];
+        const bool a0 = cc[i] < D, a1 = cc[i] > 0, b0 = rr[i] < D, b1 = rr[i] > 0, in = cell < FP;
+        i00[i] = (in && a0 && b0) ? cc[i] * D + rr[i] : ZERO;
+        i01[i] = (in && a1 && b0) ? (cc[i] - 1) * D + rr[i] : ZERO;
+        i10[i] = (in && a0 && b1) ? cc[i] * D + rr[i] - 1 : ZERO;
+        i11[i] = (in && a1 && b1) ? (cc[i] - 1) * D + rr[i] - 1 : ZERO;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < LK_TPW; ++j) {
+        if (j >= w.nq) break;                      // warp-uniform
+        const LkGeom g = lk_geom<R>(cx[j], cy[j], w);
+        const float w00 = (1.f - g.fx) * (1.f - g.fy), w01 = g.fx * (1.f - g.fy);
+        const float w10 = (1.f - g.fx) * g.fy, w11 = g.fx * g.fy;
+        const float* Gq = G[warp][j];
+        const int e = j * w.plane + g.o;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const bool ok = (32 * i + 31 < FP || lane + 32 * i < FP) &&
+                            (g.interior || ((unsigned)(g.iy0 + rr[i]) < (unsigned)w.Hl && (unsigned)(g.ix0 + cc[i]) < (unsigned)w.Wl));
+            if (ok) {
+                const float acc = fmaf(w11, Gq[i11[i]], fmaf(w10, Gq[i10[i]], fmaf(w01, Gq[i01[i]], w00 * Gq[i00[i]])));
+                red_add_policy(lvl + (e + off[i]), acc, pol);
+            }
+        }
+    }
+}
+
 }  // namespace pcfa
 
 using namespace pcfa;
@@ -208,10 +433,26 @@ static int lookup_check(const void* a, const void* b, const void* c, int B, int 
     return PCFA_OK;
 }
 
+// PCFA_LOOKUP_IMPL=1 selects the first-generation channels-last kernels; PCFA_LOOKUP_L2HINT=0 drops the evict_last policy.
+static int lookup_impl() { static const int v = [] { const char* e = getenv("PCFA_LOOKUP_IMPL"); return e ? atoi(e) : 2; }(); return v; }
+static int lookup_hint() { static const int v = [] { const char* e = getenv("PCFA_LOOKUP_L2HINT"); return e ? atoi(e) : 1; }(); return v; }
+
 static int lookup_forward(const float* pyramid, const float* coords, float* out, int B, int H, int W, int num_levels,
                           int radius, int out_cl, pcfa_stream_t stream) {
     PCFA_TRY(lookup_check(pyramid, coords, out, B, H, W, num_levels, radius));
     const PyramidLayout L = make_pyramid_layout(B, H, W, num_levels);
+    if (out_cl && (radius == 4 || radius == 3) && lookup_impl() == 2 && B <= 65535 &&
+        (int64_t)B * H * W * num_levels * (2 * radius + 1) * (2 * radius + 1) < 0x7fffffffLL) {
+        const int N = H * W;
+        dim3 grid(ceil_div(ceil_div(N, LK_TPW) * num_levels, LK_WARPS), B);
+        cudaStream_t s = as_stream(stream);
+        const int hint = lookup_hint();
+#define PCFA_LK_FWD(RR, LL) corr_lookup_fwd_cl2_kernel<RR, LL><<<grid, LK_WARPS * 32, 0, s>>>(pyramid, coords, out, L, N, hint)
+        if (radius == 4) { if (num_levels == 4) PCFA_LK_FWD(4, 4); else PCFA_LK_FWD(4, 0); }
+        else             { if (num_levels == 4) PCFA_LK_FWD(3, 4); else PCFA_LK_FWD(3, 0); }
+#undef PCFA_LK_FWD
+        return after_launch();
+    }
     const int D = 2 * radius + 1, FP = (D + 1) * (D + 1);
     const size_t smem = (size_t)QB * (FP | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);
@@ -230,6 +471,18 @@ static int lookup_backward(const float* grad_out, const float* coords, float* gr
                            int num_levels, int radius, int out_cl, pcfa_stream_t stream) {
     PCFA_TRY(lookup_check(grad_out, coords, grad_pyramid, B, H, W, num_levels, radius));
     const PyramidLayout L = make_pyramid_layout(B, H, W, num_levels);
+    if (out_cl && (radius == 4 || radius == 3) && lookup_impl() == 2 && B <= 65535 &&
+        (int64_t)B * H * W * num_levels * (2 * radius + 1) * (2 * radius + 1) < 0x7fffffffLL) {
+        const int N = H * W;
+        dim3 grid(ceil_div(ceil_div(N, LK_TPW) * num_levels, LK_WARPS), B);
+        cudaStream_t s = as_stream(stream);
+        const int hint = lookup_hint();
+#define PCFA_LK_BWD(RR, LL) corr_lookup_bwd_cl2_kernel<RR, LL><<<grid, LK_WARPS * 32, 0, s>>>(grad_out, coords, grad_pyramid, L, N, hint)
+        if (radius == 4) { if (num_levels == 4) PCFA_LK_BWD(4, 4); else PCFA_LK_BWD(4, 0); }
+        else             { if (num_levels == 4) PCFA_LK_BWD(3, 4); else PCFA_LK_BWD(3, 0); }
+#undef PCFA_LK_BWD
+        return after_launch();
+    }
     const int D = 2 * radius + 1;
     const size_t smem = (size_t)QB * ((D * D) | 1) * sizeof(float) + QB * sizeof(LookupGeom);
     dim3 grid(B * ceil_div(H * W, QB), num_levels);

@@ -342,7 +342,7 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(256, 64 * 9, 1))
 
-    def forward(self, net, inp, corr, flow, want_mask=True, cl=False, hoist=None):
+    def forward(self, net, inp, corr, flow, want_mask=True, cl=False, hoist=None, raw_mask=False):
         """cl=True: every tensor is torch.channels_last (cuDNN's sm_100 kernels are NHWC-only; with NCHW activations
         it converts around every convolution: 3 ms of the 11.8 ms RAFT closure)."""
         from ..gru_ops import cat_channels
@@ -352,7 +352,8 @@ class BasicUpdateBlock(nn.Module):
         else:
             net = self.gru(net, cat_channels([inp, motion], cl), cl)
         delta_flow = self.flow_head(net)
-        mask = 0.25 * self.mask(net) if want_mask else None     # .25 "to balance gradients" (update.py:135)
+        # .25 "to balance gradients" (update.py:135); raw_mask=True leaves it to the fused up-sampling kernel's mask_scale
+        mask = (self.mask(net) if raw_mask else 0.25 * self.mask(net)) if want_mask else None
         return net, mask, delta_flow
 
 
@@ -466,13 +467,19 @@ class RAFT(nn.Module):
             with torch.autocast(dev_type, enabled=amp):
                 if cl:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow.contiguous(memory_format=torch.channels_last),
-                                                                 want_mask=need_up, cl=True, hoist=hoist)
+                                                                 want_mask=need_up, cl=True, hoist=hoist, raw_mask=True)
                     delta_flow = delta_flow.contiguous()
                 else:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
             coords1 = coords1 + delta_flow
             if need_up:
-                flow_up = upflow8(coords1 - coords0) if up_mask is None else convex_upsample(coords1 - coords0, up_mask)
+                if up_mask is None:
+                    flow_up = upflow8(coords1 - coords0)
+                elif cl:                             # fused kernel on the raw channels-last mask (csrc/upsample.cu)
+                    from ..upsample import convex_upsample as _fused_upsample
+                    flow_up = _fused_upsample(coords1 - coords0, up_mask, 0.25)
+                else:
+                    flow_up = convex_upsample(coords1 - coords0, up_mask)
                 predictions.append(flow_up)
         if test_mode:
             return coords1 - coords0, flow_up

@@ -429,3 +429,39 @@ def test_fused_gru_elementwise_matches_torch(shape):
         outs.append((hn, zr.grad, h.grad, qp.grad))
     for name, a, b in zip(("h_new", "grad zr", "grad h", "grad q_pre"), outs[0], outs[1]):
         assert_close(npy(a), npy(b), what=name, rtol=1e-5, atol_rms=1e-6)
+
+
+# ----------------------------------------------------------------------------------- convex up-sampling (f-4)
+def _upsample_reference(flow, mask):
+    """RAFT.upsample_flow verbatim in torch ops (models/raft/raft.py:72-83)."""
+    import torch.nn.functional as F
+    N, _, H, W = flow.shape
+    mask = mask.view(N, 1, 9, 8, 8, H, W)
+    mask = torch.softmax(mask, dim=2)
+    up_flow = F.unfold(8 * flow, [3, 3], padding=1)
+    up_flow = up_flow.view(N, 2, 9, 1, 1, H, W)
+    up_flow = torch.sum(mask * up_flow, dim=2)
+    up_flow = up_flow.permute(0, 1, 4, 2, 5, 3)
+    return up_flow.reshape(N, 2, 8 * H, 8 * W)
+
+
+@pytest.mark.parametrize("shape,cl", [((1, 55, 128), True), ((2, 7, 9), True), ((2, 16, 20), False), ((1, 1, 1), True)])
+def test_convex_upsample_matches_reference_formula(shape, cl):
+    from pcfa_b200.upsample import convex_upsample
+    N, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    flow = (3 * torch.randn(N, 2, H, W, generator=g)).cuda().requires_grad_(True)
+    raw = (4 * torch.randn(N, 576, H, W, generator=g)).cuda()
+    if cl:
+        raw = raw.contiguous(memory_format=torch.channels_last)
+    raw.requires_grad_(True)
+    up = convex_upsample(flow, raw, 0.25)
+    f2, r2 = flow.detach().clone().requires_grad_(True), raw.detach().clone().contiguous().requires_grad_(True)
+    ref = _upsample_reference(f2, 0.25 * r2)
+    assert up.shape == ref.shape and up.is_contiguous()
+    assert_close(npy(up), npy(ref), what="convex upsample fwd", **TIGHT)
+    go = torch.randn(ref.shape, generator=g).cuda()
+    (up * go).sum().backward()
+    (ref * go).sum().backward()
+    assert_close(npy(flow.grad), npy(f2.grad), what="convex upsample g flow", **TIGHT)
+    assert_close(npy(raw.grad), npy(r2.grad), what="convex upsample g mask", **TIGHT)
