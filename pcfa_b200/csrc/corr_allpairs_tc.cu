@@ -22,7 +22,6 @@
 // The 1/sqrt(C) factor is folded into the query operand before the bf16 split.
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -51,7 +50,6 @@ struct TcParams {
     // 2-CTA variant: work item = (sample, pair of query blocks, pair of target tiles)
     int qb2blocks, pairs_per_qb2;
     int fuse_l1;                    // CTA-pair kernel: level 1 is pooled in the epilogue (no level-1 tiles)
-    int f16x2;                      // CTA-pair kernel: operands are fp16, 2 MMAs per k-step (see corr_pyramid_forward_tc)
     long long total_pairs;
 };
 
@@ -226,8 +224,6 @@ corr_pyramid_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams P, fl
 // (tensor pipe 49 % active).  Both CTAs run a TMA producer (loads signal the LEADER's mbarriers through the
 // .cta_group::2 form); only the leader issues MMAs; tcgen05.commit multicasts "slot free"/"accumulator full"
 // to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's barrier (remote arrive).
-// same with A = B = F16 (format field 0)
-constexpr uint32_t kIdescF16_2cta = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t kIdescBf16_2cta = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 struct PairCoord { int b, qb2, level, ty, tx; bool valid; long long key; };
@@ -308,11 +304,11 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             const int y0 = c.valid ? c.ty * TC_PH : (P.lh[0] + TC_PH), x0 = c.tx * TC_PW;
             for (int kc = 0; kc < P.kchunks; ++kc) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, (P.f16x2 ? 2 : 4) * TC_TILE_BYTES);
+                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * 2 * TC_TILE_BYTES);
                 const uint32_t dst = smem_a + stage * 2 * TC_TILE_BYTES;
                 const uint32_t lb = leader_bar(bar_full + 8 * stage);
                 tma2_load_4d(dst, &maps.t[c.level], lb, kc * TC_BK, x0, y0, c.b);
-                if (!P.f16x2) tma2_load_4d(dst + TC_TILE_BYTES, &maps.t[c.level], lb, kc * TC_BK, x0, y0, P.B + c.b);
+                tma2_load_4d(dst + TC_TILE_BYTES, &maps.t[c.level], lb, kc * TC_BK, x0, y0, P.B + c.b);
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -334,14 +330,9 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 16; ++kk) {
                     const uint32_t ko = kk * 32;
-                    if (P.f16x2) {       // targets: fp16 hi only; queries: fp16 hi + lo (exact to ~2^-22)
-                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescF16_2cta, (kc | kk) != 0);
-                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescF16_2cta, 1);
-                    } else {
-                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, (kc | kk) != 0);
-                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16_2cta, 1);
-                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_mid + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, 1);
-                    }
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, (kc | kk) != 0);
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16_2cta, 1);
+                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_mid + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, 1);
                 }
                 tc2_commit_mc(bar_empty + 8 * stage);
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -441,8 +432,6 @@ struct TcPrepArgs {
     long long plane[TC_MAX_LEVELS];        // B * H_l * W_l * C
     int h[TC_MAX_LEVELS], w[TC_MAX_LEVELS];
     int levels, B, C, skip_l1;
-    int f16;                               // 1: fp16 planes (targets hi only, scaled by tscale; queries hi + lo)
-    float tscale;
     const float* qsrc;                     // fmap1: blockIdx.z >= B*C/32 handles the query operand (level 0 only)
     __nv_bfloat16* qdst; long long qplane; float qscale;
 };
@@ -451,7 +440,7 @@ constexpr int PT_S0 = 8 * 33 + 1, PT_S1 = 4 * 17 + 1, PT_S2 = 2 * 9 + 1, PT_S3 =
 template <int LVL>
 __device__ __forceinline__ void prep_targets_drain(const float* __restrict__ t, int cstride, int rstride,
                                                    __nv_bfloat16* __restrict__ dst, long long plane, int Hl, int Wl,
-                                                   int C, int b, int c0, int y0, int x0, int f16 = 0, bool want_lo = true) {
+                                                   int C, int b, int c0, int y0, int x0) {
     constexpr int hh = 8 >> LVL, ww = 32 >> LVL, cells = hh * ww;
     for (int item = threadIdx.x; item < cells * 16; item += 256) {
         const int cp = item & 15, cell = item >> 4;
@@ -459,16 +448,9 @@ __device__ __forceinline__ void prep_targets_drain(const float* __restrict__ t, 
         const int y = (y0 >> LVL) + r, x = (x0 >> LVL) + q;
         if (y >= Hl || x >= Wl) continue;
         const float v0 = t[(2 * cp) * cstride + r * rstride + q], v1 = t[(2 * cp + 1) * cstride + r * rstride + q];
-        const long long o = (((long long)b * Hl + y) * Wl + x) * C + c0 + 2 * cp;
-        if (f16) {                                   // same 2-byte storage, fp16 encoding
-            const __half2 hi = __floats2half2_rn(v0, v1);
-            *reinterpret_cast<__half2*>(dst + o) = hi;
-            if (want_lo)
-                *reinterpret_cast<__half2*>(dst + plane + o) = __floats2half2_rn(v0 - __low2float(hi), v1 - __high2float(hi));
-            continue;
-        }
         const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
         const __nv_bfloat162 mid = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+        const long long o = (((long long)b * Hl + y) * Wl + x) * C + c0 + 2 * cp;
         *reinterpret_cast<__nv_bfloat162*>(dst + o) = hi;
         *reinterpret_cast<__nv_bfloat162*>(dst + plane + o) = mid;
     }
@@ -493,7 +475,7 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
         const bool inb = y < H && x < W;
         const float* p = (qside ? a.qsrc : src) + (((long long)b * a.C + c0) * H + y) * W + x;
         const long long cs = (long long)H * W;
-        const float sc = qside ? a.qscale : a.tscale;
+        const float sc = qside ? a.qscale : 1.f;
         float v[32];                                                  // all 32 loads in flight
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = inb ? __ldg(p + c * cs) * sc : 0.f;
@@ -502,7 +484,7 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
     }
     __syncthreads();
     if (qside) {
-        prep_targets_drain<0>(t0, PT_S0, 33, a.qdst, a.qplane, H, W, a.C, b, c0, y0, x0, a.f16, true);
+        prep_targets_drain<0>(t0, PT_S0, 33, a.qdst, a.qplane, H, W, a.C, b, c0, y0, x0);
         return;
     }
     for (int e = threadIdx.x; e < 32 * 64; e += 256) {
@@ -523,10 +505,10 @@ prep_targets_kernel(const float* __restrict__ src, const TcPrepArgs a) {
         t3[c * PT_S3 + q] = 0.25f * ((s2[0] + s2[1]) + (s2[9] + s2[10]));
     }
     __syncthreads();
-    prep_targets_drain<0>(t0, PT_S0, 33, a.dst[0], a.plane[0], a.h[0], a.w[0], a.C, b, c0, y0, x0, a.f16, false);
-    if (a.levels > 1 && !a.skip_l1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0, a.f16, false);
-    if (a.levels > 2) prep_targets_drain<2>(t2, PT_S2, 9, a.dst[2], a.plane[2], a.h[2], a.w[2], a.C, b, c0, y0, x0, a.f16, false);
-    if (a.levels > 3) prep_targets_drain<3>(t3, PT_S3, 5, a.dst[3], a.plane[3], a.h[3], a.w[3], a.C, b, c0, y0, x0, a.f16, false);
+    prep_targets_drain<0>(t0, PT_S0, 33, a.dst[0], a.plane[0], a.h[0], a.w[0], a.C, b, c0, y0, x0);
+    if (a.levels > 1 && !a.skip_l1) prep_targets_drain<1>(t1, PT_S1, 17, a.dst[1], a.plane[1], a.h[1], a.w[1], a.C, b, c0, y0, x0);
+    if (a.levels > 2) prep_targets_drain<2>(t2, PT_S2, 9, a.dst[2], a.plane[2], a.h[2], a.w[2], a.C, b, c0, y0, x0);
+    if (a.levels > 3) prep_targets_drain<3>(t3, PT_S3, 5, a.dst[3], a.plane[3], a.h[3], a.w[3], a.C, b, c0, y0, x0);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -603,19 +585,11 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     // ---- operand preparation: channel-last bf16 hi/mid copies of fmap1 and of pool_l(fmap2)
     static const int env_fuse = [] { const char* e = getenv("PCFA_FWD_FUSE_L1"); return e ? atoi(e) : 1; }();
     const int fuse_l1 = (two_cta && levels >= 2 && env_fuse) ? 1 : 0;
-    // Operand arithmetic of the CTA-pair kernel (PCFA_FWD_MODE): 0 = bf16 x 3 (hi*hi + hi*mid + mid*hi, ~1e-5 relative),
-    // 1 = fp16 x 2: the streamed target operand is ONE fp16 term (11-bit significand, 1/sqrt(C) folded in), the resident
-    // query operand is fp16 hi + lo (exact to ~2^-22), i.e. the only rounding beyond fp32 is the target's 2^-12 half-ulp:
-    // rel-L2 1.4e-4 on the volume at 2/3 of the tensor work and half the operand stream.  fp16 saturates at 65504:
-    // features are O(1-10) after RAFT's instance-normalised encoder; mode 0 has no such limit.
-    static const int env_mode = [] { const char* e = getenv("PCFA_FWD_MODE"); return e ? atoi(e) : 0; }();
-    const int f16x2 = (two_cta && env_mode == 1) ? 1 : 0;
     {
         TcPrepArgs pa{};
         pa.levels = levels; pa.B = B; pa.C = C; pa.skip_l1 = fuse_l1;
-        pa.f16 = f16x2; pa.tscale = f16x2 ? 1.0f / sqrtf((float)C) : 1.f;
         pa.qsrc = fmap1; pa.qdst = reinterpret_cast<__nv_bfloat16*>(wsb + wl.q_split);
-        pa.qplane = (long long)B * N * C; pa.qscale = f16x2 ? 1.f : 1.0f / sqrtf((float)C);
+        pa.qplane = (long long)B * N * C; pa.qscale = 1.0f / sqrtf((float)C);
         for (int l = 0; l < levels; ++l) {
             pa.dst[l] = reinterpret_cast<__nv_bfloat16*>(wsb + wl.t_split[l]);
             pa.plane[l] = (long long)B * L.h[l] * L.w[l] * C;
@@ -642,7 +616,6 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     P.B = B; P.N = N; P.levels = levels; P.kchunks = C / TC_BK; P.qblocks = ceil_div(N, TC_BN);
     P.scale = 1.0f / sqrtf((float)C);
     P.fuse_l1 = fuse_l1;
-    P.f16x2 = f16x2;
     int toff = 0;
     for (int l = 0; l < levels; ++l) {
         P.lh[l] = L.h[l]; P.lw[l] = L.w[l]; P.lvl_off[l] = L.off[l];

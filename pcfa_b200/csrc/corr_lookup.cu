@@ -254,6 +254,14 @@ __device__ __forceinline__ LkWarp lk_warp(int gw, int b, int N, const PyramidLay
     return w;
 }
 
+// base + idx as ONE IMAD.WIDE (the compiler otherwise re-derives 64-bit sums with carry chains for every access)
+template <typename T>
+__device__ __forceinline__ T* ptr_add(T* base, int idx) {
+    uint64_t r;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<T*>(r);
+}
+
 struct LkGeom { int o; float fx, fy; bool interior; int iy0, ix0; };
 
 template <int R>
@@ -287,49 +295,42 @@ corr_lookup_fwd_cl2_kernel(const float* __restrict__ pyramid, const float* __res
     const float* lvl = pyramid + w.lvl_off;
     const float* cxp = coords + ((int64_t)b * 2 * N + w.q0);
 
-    int off[NLD];                                  // per-lane element offset of cell lane+32i inside a footprint
+    int rr[NLD], cc[NLD], off[NLD];                // per-lane (row, col) and element offset of cell lane+32i inside a footprint
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
-        const int cell = lane + 32 * i, r_ = cell / F;
-        off[i] = r_ * w.Wl + (cell - r_ * F);
+        const int cell = lane + 32 * i;
+        rr[i] = cell / F; cc[i] = cell - rr[i] * F;
+        if (cell >= FP) rr[i] = 1 << 20;           // never in range
+        off[i] = rr[i] * w.Wl + cc[i];
     }
     float cx[LK_TPW], cy[LK_TPW];
 #pragma unroll
     for (int j = 0; j < LK_TPW; ++j) {
         const int jj = min(j, w.nq - 1);
-        cx[j] = cxp[jj];
-        cy[j] = cxp[N + jj];
+        cx[j] = *ptr_add(cxp, jj);
+        cy[j] = *ptr_add(cxp, N + jj);
     }
+    // Levels 2 and 3 (13x32, 6x16 at 55x128) never contain a whole 10x10 footprint, so every load is bounds-checked:
+    // rows [rlo, rhi) and columns [clo, chi) of the footprint lie inside the level (one subtract + one compare each).
     float v[LK_TPW][NLD];
-    bool inside[LK_TPW];
 #pragma unroll
     for (int j = 0; j < LK_TPW; ++j) {
         const LkGeom g = lk_geom<R>(cx[j], cy[j], w);
         if (lane == 0) { S[warp][j][FP] = g.fx; S[warp][j][FP + 1] = g.fy; }
         const int e = min(j, w.nq - 1) * w.plane + g.o;
-        inside[j] = g.interior;
-        if (g.interior) {                          // warp-uniform: footprint inside the level (the common case)
+        const int rlo = max(0, -g.iy0), clo = max(0, -g.ix0);
+        const unsigned rn = (unsigned)max(0, min(F, w.Hl - g.iy0) - rlo), cn = (unsigned)max(0, min(F, w.Wl - g.ix0) - clo);
 #pragma unroll
-            for (int i = 0; i < NLD; ++i)
-                v[j][i] = (32 * i + 31 < FP || lane + 32 * i < FP) ? ldg_policy(lvl + (e + off[i]), pol) : 0.f;
-        } else {                                   // rare: bounds-checked, staged directly
-#pragma unroll 1
-            for (int cell = lane; cell < FP; cell += 32) {
-                const int r_ = cell / F, c_ = cell - r_ * F;
-                const bool ok = (unsigned)(g.iy0 + r_) < (unsigned)w.Hl && (unsigned)(g.ix0 + c_) < (unsigned)w.Wl;
-                S[warp][j][cell] = ok ? ldg_policy(lvl + (e + r_ * w.Wl + c_), pol) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) v[j][i] = 0.f;
+        for (int i = 0; i < NLD; ++i) {
+            const bool ok = (unsigned)(rr[i] - rlo) < rn && (unsigned)(cc[i] - clo) < cn;
+            v[j][i] = ok ? ldg_policy(ptr_add(lvl, e + off[i]), pol) : 0.f;
         }
     }
 #pragma unroll
     for (int j = 0; j < LK_TPW; ++j)
-        if (inside[j]) {
 #pragma unroll
-            for (int i = 0; i < NLD; ++i)
-                if (32 * i + 31 < FP || lane + 32 * i < FP) S[warp][j][lane + 32 * i] = v[j][i];
-        }
+        for (int i = 0; i < NLD; ++i)
+            if (32 * i + 31 < FP || lane + 32 * i < FP) S[warp][j][lane + 32 * i] = v[j][i];
     __syncwarp();
 
     int toff[NOUT];                                // output channel -> top-left cell of its 2x2 taps
@@ -350,7 +351,7 @@ corr_lookup_fwd_cl2_kernel(const float* __restrict__ pyramid, const float* __res
         for (int i = 0; i < NOUT; ++i) {
             if (32 * i + 31 < NCH || lane + 32 * i < NCH) {
                 const float* p = Sq + toff[i];
-                o[j * CT + 32 * i] = w00 * p[0] + w01 * p[1] + w10 * p[F] + w11 * p[F + 1];
+                ptr_add(o, j * CT)[32 * i] = w00 * p[0] + w01 * p[1] + w10 * p[F] + w11 * p[F + 1];
             }
         }
     }
@@ -379,11 +380,11 @@ corr_lookup_bwd_cl2_kernel(const float* __restrict__ gout, const float* __restri
 #pragma unroll
     for (int j = 0; j < LK_TPW; ++j) {
         const int jj = min(j, w.nq - 1);
-        cx[j] = cxp[jj];
-        cy[j] = cxp[N + jj];
+        cx[j] = *ptr_add(cxp, jj);
+        cy[j] = *ptr_add(cxp, N + jj);
 #pragma unroll
         for (int i = 0; i < NOUT; ++i)
-            if (32 * i + 31 < NCH || lane + 32 * i < NCH) G[warp][j][lane + 32 * i] = __ldg(gi + (jj * CT + 32 * i));
+            if (32 * i + 31 < NCH || lane + 32 * i < NCH) G[warp][j][lane + 32 * i] = __ldg(ptr_add(gi, jj * CT) + 32 * i);
         if (lane == 0) G[warp][j][ZERO] = 0.f;
     }
     // cell (rr, cc) receives tap (a=cc, b=rr)*w00 + (cc-1, rr)*w01 + (cc, rr-1)*w10 + (cc-1, rr-1)*w11; tap (a, b) is channel a*D + b
@@ -414,7 +415,7 @@ corr_lookup_bwd_cl2_kernel(const float* __restrict__ gout, const float* __restri
                             (g.interior || ((unsigned)(g.iy0 + rr[i]) < (unsigned)w.Hl && (unsigned)(g.ix0 + cc[i]) < (unsigned)w.Wl));
             if (ok) {
                 const float acc = fmaf(w11, Gq[i11[i]], fmaf(w10, Gq[i10[i]], fmaf(w01, Gq[i01[i]], w00 * Gq[i00[i]])));
-                red_add_policy(lvl + (e + off[i]), acc, pol);
+                red_add_policy(ptr_add(lvl, e + off[i]), acc, pol);
             }
         }
     }

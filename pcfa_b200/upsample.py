@@ -13,7 +13,8 @@ class _ConvexUpsample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flow, mask, mask_scale):
         lib = _lib.load()
-        _lib.require_cuda(flow, mask, name="convex_upsample")
+        if not (flow.is_cuda and mask.is_cuda):
+            raise RuntimeError("convex_upsample: expected CUDA tensors (pcfa_b200 has no CPU path), got %s / %s" % (flow.device, mask.device))
         N, two, H, W = flow.shape
         if two != 2 or tuple(mask.shape) != (N, 576, H, W):
             raise ValueError("convex_upsample: flow [N,2,H,W] and mask [N,576,H,W] expected, got %s and %s"
