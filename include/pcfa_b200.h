@@ -342,6 +342,15 @@ int pcfa_convex_upsample_backward(const float* flow, const float* mask_cl, const
                                   float* grad_mask_cl, void* workspace, int64_t workspace_bytes, int N, int H, int W,
                                   float mask_scale, pcfa_stream_t stream);
 
+/* --------------------------------------------------------------------------- GMA attention softmax
+ * attn = softmax(sim, dim=-1) of models/gma/gma.py:73-74 for the shipped fp16-autocast configuration: fp16 rows in,
+ * fp16 rows out, fp32 arithmetic (what the reference's fp32 softmax followed by the aggregation GEMM's fp16 cast yields).
+ *   sim, attn, grad_*: [rows][cols] __half, 16-byte aligned, cols % 8 == 0 and cols <= 16384 (else PCFA_E_BADARG).
+ * backward: grad_sim = attn * (grad_attn - sum_j attn_j * grad_attn_j). */
+int pcfa_softmax_rows_f16_forward(const void* sim, void* attn, int64_t rows, int cols, pcfa_stream_t stream);
+int pcfa_softmax_rows_f16_backward(const void* attn, const void* grad_attn, void* grad_sim, int64_t rows, int cols,
+                                   pcfa_stream_t stream);
+
 /* --------------------------------------------------------------------------- on-device L-BFGS
  * The vector algebra of torch.optim.LBFGS.step (torch/optim/lbfgs.py; the reference's optimiser, attack_PCFA.py:97,114)
  * without its ~4*history ATen launches per iteration.  History: ring buffers S, Y of [history_capacity][n] floats.

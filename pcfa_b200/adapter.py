@@ -128,6 +128,13 @@ def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = 
         if net == "RAFT" and channels_last_update:             # NHWC update block: networks/raft.py, BasicUpdateBlock.forward
             model.update_block.to(memory_format=torch.channels_last)
             model.update_block.channels_last = True
+        if net == "GMA" and channels_last_update:              # networks/gma.py: NHWC update block, attention on views
+            model.update_block.to(memory_format=torch.channels_last)
+            model.att.to(memory_format=torch.channels_last)
+            model.update_block.channels_last = True
+        if net == "GMA":
+            from .networks.amp import install_frozen_half_weights
+            install_frozen_half_weights(model)
     return model
 
 

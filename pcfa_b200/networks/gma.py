@@ -53,7 +53,13 @@ class Attention(nn.Module):
             sim = einsum('b h x y d, b h u v d -> b h x y u v', q, k)
             if self.position_and_content:
                 sim = sim + self.pos_emb(q)
-        return sim.reshape(b, self.heads, h * w, h * w).softmax(dim=-1)
+        sim = sim.reshape(b, self.heads, h * w, h * w)
+        from ..attention import softmax_rows_f16, softmax_rows_supported
+        if softmax_rows_supported(sim):
+            # fp16 autocast (the shipped configuration): one fused pass, fp16 in / fp16 out, fp32 arithmetic — the
+            # values the aggregation GEMMs consume in the reference (fp32 softmax, cast to fp16 by every einsum)
+            return softmax_rows_f16(sim)
+        return sim.softmax(dim=-1)
 
 
 class Aggregate(nn.Module):
@@ -68,7 +74,17 @@ class Aggregate(nn.Module):
 
     def forward(self, attn, fmap):
         b, _, h, w = fmap.shape
-        v = self.to_v(fmap).view(b, self.heads, -1, h * w).transpose(2, 3)          # b h (x y) d
+        v = self.to_v(fmap)
+        if self.heads == 1 and v.is_cuda and v.is_contiguous(memory_format=torch.channels_last) and not v.is_contiguous():
+            # channels-last memory IS 'b (x y) d': the aggregation is one batched GEMM on views, no copies either side
+            vm = v.permute(0, 2, 3, 1).reshape(b, h * w, -1)
+            a2 = attn.reshape(b, h * w, h * w)
+            out = torch.bmm(a2.to(vm.dtype) if a2.dtype != vm.dtype else a2, vm)
+            out = out.view(b, h, w, -1).permute(0, 3, 1, 2)                         # channels-last [b, d, h, w]
+            if self.project is not None:
+                out = self.project(out)
+            return fmap + self.gamma * out
+        v = v.reshape(b, self.heads, -1, h * w).transpose(2, 3)                     # b h (x y) d
         out = einsum('b h i j, b h j d -> b h i d', attn, v)
         out = out.transpose(2, 3).reshape(b, -1, h, w)                              # b (h d) x y
         if self.project is not None:
@@ -85,12 +101,14 @@ class GMAUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
         self.aggregator = Aggregate(dim=128, dim_head=128, heads=num_heads)
 
-    def forward(self, net, inp, corr, flow, attention, want_mask=True):
+    def forward(self, net, inp, corr, flow, attention, want_mask=True, raw_mask=False):
+        """With channels-last inputs (and channels-last weights, adapter.build_network) every tensor stays NHWC: cuDNN's
+        sm_100 kernels are NHWC-only and otherwise convert around each of the ~17 convolutions per iteration."""
         motion = self.encoder(flow, corr)
         motion_global = self.aggregator(attention, motion)
         net = self.gru(net, torch.cat([inp, motion, motion_global], dim=1))
         delta_flow = self.flow_head(net)
-        mask = 0.25 * self.mask(net) if want_mask else None
+        mask = (self.mask(net) if raw_mask else 0.25 * self.mask(net)) if want_mask else None
         return net, mask, delta_flow
 
 
@@ -135,16 +153,27 @@ class RAFTGMA(nn.Module):
         if flow_init is not None:
             coords1 = coords1 + flow_init
         predictions, flow_up = [], None
+        from ..corr_block import CorrBlock as _OwnCorrBlock
+        cl = (bool(getattr(self.update_block, "channels_last", False)) and dev_type == "cuda"
+              and isinstance(corr_fn, _OwnCorrBlock))
+        if cl:
+            net = net.contiguous(memory_format=torch.channels_last)
+            inp = inp.contiguous(memory_format=torch.channels_last)
         for itr in range(iters):
             coords1 = coords1.detach()
-            corr = corr_fn(coords1)
+            corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
             flow = coords1 - coords0
             need_up = (not test_mode) or itr == iters - 1
             with torch.autocast(dev_type, enabled=amp):
-                net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, attention, want_mask=need_up)
-            coords1 = coords1 + delta_flow
+                fl = flow.contiguous(memory_format=torch.channels_last) if cl else flow
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, fl, attention, want_mask=need_up, raw_mask=cl)
+            coords1 = coords1 + delta_flow.float().contiguous()
             if need_up:
-                flow_up = convex_upsample(coords1 - coords0, up_mask)
+                if cl:                                 # fused kernel on the raw mask (csrc/upsample.cu), fp32 like the reference's
+                    from ..upsample import convex_upsample as _fused_upsample      # fp32 softmax under autocast
+                    flow_up = _fused_upsample(coords1 - coords0, up_mask, 0.25)
+                else:
+                    flow_up = convex_upsample(coords1 - coords0, up_mask)
                 predictions.append(flow_up)
         if test_mode:
             return coords1 - coords0, flow_up

@@ -76,6 +76,9 @@ def _conv_norm_act(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool
     if (x.is_cuda and isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats and frozen
             and conv.padding_mode == "zeros"):
         w, b = _bn_folded(conv, norm)
+        from .amp import amp_half_active, half_params
+        if amp_half_active(x):                                # frozen weights: autocast would re-cast them on every call
+            w, b = half_params(conv, w, b, "_pcfa_bn_fold16")
         y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
         return F.relu(y) if relu else y
     return _norm_act(norm, conv(x), relu)

@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one eager RAFT closure with torch.profiler (CUPTI; no serialisation, warm caches).
-usage: python scripts/profile_closure.py [nchw|cl] [topN]"""
+usage: python scripts/profile_closure.py [nchw|cl] [topN] [RAFT|GMA] [batch]"""
 import sys, collections, torch
 sys.path.insert(0, '.')
 import bench
@@ -10,12 +10,22 @@ topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 _lib.load()
 device = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
-net, i1, i2 = bench.make_problem(device, 0, 436, 1024)
+name = sys.argv[3] if len(sys.argv) > 3 else "RAFT"
+batch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+if name == "RAFT":
+    net, i1, i2 = bench.make_problem(device, 0, 436, 1024)
+else:
+    from pcfa_b200.adapter import build_network
+    from pcfa_b200.networks.weights import synthetic_pair
+    net = build_network(name, device=device, seed=0)
+    prs = [synthetic_pair(i, 436, 1024) for i in range(batch)]
+    i1, i2 = torch.cat([p[0] for p in prs]), torch.cat([p[1] for p in prs])
 if fmt == "cl":
     net = net.to(memory_format=torch.channels_last)
 padder, img1, img2 = bench.prepare_on_device(i1.pin_memory(), i2.pin_memory(), device)
-target = torch.zeros(1, 2, 436, 1024, device=device)
-fo = J.FusedObjective(lambda a, b: net(a, b, iters=12, test_mode=True)[1], img1, img2, target, mode=J.BOX_COV, joint=False,
+target = torch.zeros(img1.shape[0], 2, 436, 1024, device=device)
+iters = 12 if name == "RAFT" else 6
+fo = J.FusedObjective(lambda a, b: net(a, b, iters=iters, test_mode=True)[1], img1, img2, target, mode=J.BOX_COV, joint=False,
                       pad=padder.top_left, eps_box=bench.EPS_BOX, scale=255.0, delta_bound=bench.DELTA_BOUND, mu=bench.MU, loss="aee")
 w1, w2 = bench.init_vars(img1), bench.init_vars(img2)
 g1, g2 = torch.empty_like(w1), torch.empty_like(w2)

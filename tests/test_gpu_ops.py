@@ -465,3 +465,27 @@ def test_convex_upsample_matches_reference_formula(shape, cl):
     (ref * go).sum().backward()
     assert_close(npy(flow.grad), npy(f2.grad), what="convex upsample g flow", **TIGHT)
     assert_close(npy(raw.grad), npy(r2.grad), what="convex upsample g mask", **TIGHT)
+
+
+# ----------------------------------------------------------------------------------- GMA attention softmax (f-2)
+@pytest.mark.parametrize("rows,cols", [(7040, 7040), (33, 1000), (5, 16384), (2, 8)])
+def test_softmax_rows_f16_matches_fp32_softmax_of_the_fp16_input(rows, cols):
+    """models/gma/gma.py:73-74 under fp16 autocast: softmax(sim) is computed in fp32 from the fp16 similarity and cast
+    to fp16 by the consumer; the fused kernel must return exactly that rounding (<= 1 fp16 ulp), and its backward
+    attn * (g - <attn, g>) from the same fp16 tensors."""
+    from pcfa_b200.attention import softmax_rows_f16
+    g = torch.Generator().manual_seed(rows + cols)
+    sim = (4 * torch.randn(rows, cols, generator=g)).half().cuda().requires_grad_(True)
+    attn = softmax_rows_f16(sim)
+    ref = torch.softmax(sim.detach().float(), dim=-1)
+    assert attn.dtype == torch.float16 and attn.shape == sim.shape
+    err = (attn.float() - ref).abs()
+    assert float((err - 1e-3 * ref).max()) <= 1e-7, float(err.max())          # fp16 rounding of the fp32 result: 2^-11 relative
+    np.testing.assert_allclose(attn.detach().float().sum(-1).cpu().numpy(), 1.0, rtol=2e-3)
+    go = torch.randn(rows, cols, generator=g).half().cuda()
+    (attn * go).sum().backward()
+    a32, g32 = attn.detach().float(), go.float()
+    want = a32 * (g32 - (a32 * g32).sum(-1, keepdim=True))
+    got = sim.grad.float()
+    scale = float(want.abs().max()) + 1e-30
+    assert float((got - want).abs().max()) <= 2e-3 * scale
