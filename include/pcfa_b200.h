@@ -322,6 +322,20 @@ int pcfa_gru_blend_x_forward(const float* z, const float* q_pre, const float* ad
 int pcfa_gru_blend_x_backward(const float* z, const float* q, const float* h, const float* grad_h_new, const float* grad_hm,
                               float* grad_z, float* grad_q_pre, float* grad_h, int C, int Cm, int64_t npix, pcfa_stream_t stream);
 
+/* Whole-step variants for one autograd node per SepConvGRU step (pcfa_b200/gru_ops.py::gru_step_x):
+ *   *_backward_acc : as above, with a second dense addend for grad_h_new and an accumulator for the gradient of the hoisted
+ *                    addend (acc_mode 0 none, 1 acc = grad, 2 acc += grad; summed over the GRU iterations in place);
+ *   pcfa_gru_step_combine : grad_h = gh_a + gh_b + cat0[:, :C];  grad_m = sum_k cat_k[:, C:]  over the four [npix][C+Cm]
+ *                    gradients of the step's concatenated convolution inputs — every gradient is written once. */
+int pcfa_gru_gates_x_backward_acc(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rhm,
+                                  float* grad_zr, float* grad_h, float* acc, int acc_mode, int C, int Cm, int64_t npix,
+                                  pcfa_stream_t stream);
+int pcfa_gru_blend_x_backward_acc(const float* z, const float* q, const float* h, const float* grad_h_new_a, const float* grad_h_new_b,
+                                  const float* grad_hm, float* grad_z, float* grad_q_pre, float* grad_h, float* acc, int acc_mode,
+                                  int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_step_combine(const float* gh_a, const float* gh_b, const float* cat0, const float* cat1, const float* cat2,
+                          const float* cat3, float* grad_h, float* grad_m, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+
 /* Channel concatenation of up to four channels-last tensors [npix][C_k] -> [npix][sum C_k] (torch.cat(dim=1) of
  * torch.channels_last tensors, which ATen runs on a slow path). */
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,

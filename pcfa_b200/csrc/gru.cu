@@ -225,6 +225,89 @@ gru_blend_x_bwd_kernel(const float* __restrict__ z, const float* __restrict__ q,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-GRU-step backward helpers (pcfa_b200/gru_ops.py::gru_step_x): the two half steps of SepConvGRU share h and the
+// motion features m between five consumers each, and autograd sums their gradients one strided ATen add at a time
+// (~14 launches, 6 us each, per GRU iteration; 1.0 ms of the 8.6 ms RAFT closure).  With one autograd node per step
+// the sums happen inside these kernels and every gradient is written once.
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// acc_mode: 0 no accumulator, 1 acc = value, 2 acc += value (gradient of the hoisted addend, summed over iterations)
+__device__ __forceinline__ void acc4(float* acc, int mode, float4 v) {
+    if (mode == 1) *reinterpret_cast<float4*>(acc) = v;
+    else if (mode == 2) { float4* a = reinterpret_cast<float4*>(acc); *a = f4add(*a, v); }
+}
+
+// like gru_gates_x_bwd_kernel, plus the addend accumulator acc [npix][2C]
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_gates_x_bwd2_kernel(const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ h,
+                        const float* __restrict__ gz, const float* __restrict__ grhm, float* __restrict__ gzr,
+                        float* __restrict__ gh, float* __restrict__ acc, int acc_mode, GruX g) {
+    const int QC = g.C >> 2;
+    const int64_t total = g.npix * QC;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / QC;
+        const int qd = (int)(e - p * QC);
+        const float4 zz = ld4(z + p * g.C + 4 * qd), rr = ld4(r + p * g.C + 4 * qd), hv = ld4(h + p * g.C + 4 * qd);
+        const float4 a = ld4(gz + p * g.C + 4 * qd), b = ld4(grhm + p * (g.C + g.Cm) + 4 * qd);
+        const float4 o1 = make_float4(a.x * zz.x * (1.f - zz.x), a.y * zz.y * (1.f - zz.y), a.z * zz.z * (1.f - zz.z), a.w * zz.w * (1.f - zz.w));
+        const float4 o2 = make_float4(b.x * hv.x * rr.x * (1.f - rr.x), b.y * hv.y * rr.y * (1.f - rr.y), b.z * hv.z * rr.z * (1.f - rr.z),
+                                      b.w * hv.w * rr.w * (1.f - rr.w));
+        reinterpret_cast<float4*>(gzr + p * 2 * g.C)[qd] = o1;
+        reinterpret_cast<float4*>(gzr + p * 2 * g.C + g.C)[qd] = o2;
+        acc4(acc + p * 2 * g.C + 4 * qd, acc_mode, o1);
+        acc4(acc + p * 2 * g.C + g.C + 4 * qd, acc_mode, o2);
+        reinterpret_cast<float4*>(gh + p * g.C)[qd] = make_float4(b.x * rr.x, b.y * rr.y, b.z * rr.z, b.w * rr.w);
+    }
+}
+
+// total grad of h_new = ghn_a + ghn_b (may be NULL) + ghm[:, :C] (may be NULL); acc [npix][C] accumulates grad_q_pre
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_blend_x_bwd2_kernel(const float* __restrict__ z, const float* __restrict__ q, const float* __restrict__ h,
+                        const float* __restrict__ ghn_a, const float* __restrict__ ghn_b, const float* __restrict__ ghm,
+                        float* __restrict__ gz, float* __restrict__ gq, float* __restrict__ gh, float* __restrict__ acc, int acc_mode,
+                        GruX g) {
+    const int QC = g.C >> 2;
+    const int64_t total = g.npix * QC;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / QC;
+        const int qd = (int)(e - p * QC);
+        float4 d = ld4(ghn_a + p * g.C + 4 * qd);
+        if (ghn_b) d = f4add(d, ld4(ghn_b + p * g.C + 4 * qd));
+        if (ghm) d = f4add(d, ld4(ghm + p * (g.C + g.Cm) + 4 * qd));
+        const float4 zz = ld4(z + p * g.C + 4 * qd), qq = ld4(q + p * g.C + 4 * qd), hv = ld4(h + p * g.C + 4 * qd);
+        reinterpret_cast<float4*>(gz + p * g.C)[qd] = make_float4(d.x * (qq.x - hv.x), d.y * (qq.y - hv.y), d.z * (qq.z - hv.z), d.w * (qq.w - hv.w));
+        const float4 o = make_float4(d.x * zz.x * (1.f - qq.x * qq.x), d.y * zz.y * (1.f - qq.y * qq.y),
+                                     d.z * zz.z * (1.f - qq.z * qq.z), d.w * zz.w * (1.f - qq.w * qq.w));
+        reinterpret_cast<float4*>(gq + p * g.C)[qd] = o;
+        acc4(acc + p * g.C + 4 * qd, acc_mode, o);
+        reinterpret_cast<float4*>(gh + p * g.C)[qd] = make_float4(d.x * (1.f - zz.x), d.y * (1.f - zz.y), d.z * (1.f - zz.z), d.w * (1.f - zz.w));
+    }
+}
+
+// grad_h = gh_a + gh_b + cat0[:, :C];  grad_m = cat0[:, C:] + cat1[:, C:] + cat2[:, C:] + cat3[:, C:]
+// (cat_k are the [npix][C+Cm] gradients of the concatenated convolution inputs of the step)
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_step_combine_kernel(const float* __restrict__ gh_a, const float* __restrict__ gh_b, const float* __restrict__ cat0,
+                        const float* __restrict__ cat1, const float* __restrict__ cat2, const float* __restrict__ cat3,
+                        float* __restrict__ gh, float* __restrict__ gm, GruX g) {
+    const int QC = g.C >> 2, Q = (g.C + g.Cm) >> 2, CT = g.C + g.Cm;
+    const int64_t total = g.npix * Q;
+    for (int64_t e = (int64_t)blockIdx.x * GRU_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * GRU_THREADS) {
+        const int64_t p = e / Q;
+        const int qd = (int)(e - p * Q);
+        const float4 c0 = ld4(cat0 + p * CT + 4 * qd);
+        if (qd < QC) {
+            reinterpret_cast<float4*>(gh + p * g.C)[qd] = f4add(f4add(ld4(gh_a + p * g.C + 4 * qd), ld4(gh_b + p * g.C + 4 * qd)), c0);
+        } else {
+            const float4 s = f4add(f4add(c0, ld4(cat1 + p * CT + 4 * qd)), f4add(ld4(cat2 + p * CT + 4 * qd), ld4(cat3 + p * CT + 4 * qd)));
+            reinterpret_cast<float4*>(gm + p * g.Cm)[qd - QC] = s;
+        }
+    }
+}
+
 static int gru_grid(int64_t n, int vec) {
     const int64_t per = (int64_t)GRU_THREADS * (vec ? 4 : 1);
     int64_t b = (n + per - 1) / per;
@@ -356,5 +439,35 @@ extern "C" int pcfa_gru_blend_x_backward(const float* z, const float* q, const f
     const GruX g{C, Cm, npix};
     gru_blend_x_bwd_kernel<<<gru_grid(npix * C, 1), GRU_THREADS, 0, as_stream(stream)>>>(z, q, h, grad_h_new, grad_hm, grad_z, grad_q_pre,
                                                                                         grad_h, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_gates_x_backward_acc(const float* z, const float* r, const float* h, const float* grad_z, const float* grad_rhm,
+                                             float* grad_zr, float* grad_h, float* acc, int acc_mode, int C, int Cm, int64_t npix,
+                                             pcfa_stream_t stream) {
+    if (!z || !r || !h || !grad_z || !grad_rhm || !grad_zr || !grad_h || acc_mode < 0 || acc_mode > 2 || (acc_mode && !acc)) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {z, r, h, grad_z, grad_rhm, grad_zr, grad_h, acc}));
+    const GruX g{C, Cm, npix};
+    gru_gates_x_bwd2_kernel<<<gru_grid(npix * C, 1), GRU_THREADS, 0, as_stream(stream)>>>(z, r, h, grad_z, grad_rhm, grad_zr, grad_h, acc, acc_mode, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_blend_x_backward_acc(const float* z, const float* q, const float* h, const float* grad_h_new_a,
+                                             const float* grad_h_new_b, const float* grad_hm, float* grad_z, float* grad_q_pre,
+                                             float* grad_h, float* acc, int acc_mode, int C, int Cm, int64_t npix, pcfa_stream_t stream) {
+    if (!z || !q || !h || !grad_h_new_a || !grad_z || !grad_q_pre || !grad_h || acc_mode < 0 || acc_mode > 2 || (acc_mode && !acc)) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {z, q, h, grad_h_new_a, grad_h_new_b, grad_hm, grad_z, grad_q_pre, grad_h, acc}));
+    const GruX g{C, Cm, npix};
+    gru_blend_x_bwd2_kernel<<<gru_grid(npix * C, 1), GRU_THREADS, 0, as_stream(stream)>>>(z, q, h, grad_h_new_a, grad_h_new_b, grad_hm, grad_z,
+                                                                                         grad_q_pre, grad_h, acc, acc_mode, g);
+    return after_launch();
+}
+
+extern "C" int pcfa_gru_step_combine(const float* gh_a, const float* gh_b, const float* cat0, const float* cat1, const float* cat2,
+                                     const float* cat3, float* grad_h, float* grad_m, int C, int Cm, int64_t npix, pcfa_stream_t stream) {
+    if (!gh_a || !gh_b || !cat0 || !cat1 || !cat2 || !cat3 || !grad_h || !grad_m || Cm <= 0) return PCFA_E_BADARG;
+    PCFA_TRY(grux_check(C, Cm, npix, {gh_a, gh_b, cat0, cat1, cat2, cat3, grad_h, grad_m}));
+    const GruX g{C, Cm, npix};
+    gru_step_combine_kernel<<<gru_grid(npix * (C + Cm), 1), GRU_THREADS, 0, as_stream(stream)>>>(gh_a, gh_b, cat0, cat1, cat2, cat3, grad_h, grad_m, g);
     return after_launch();
 }

@@ -198,3 +198,125 @@ def gru_gates_x(zr, addend, h, m):
 
 def gru_blend_x(z, q_pre, addend, h, m, make_hm: bool):
     return _BlendX.apply(z, q_pre, addend, h, m, make_hm)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# One autograd node per SepConvGRU step (horizontal + vertical half step) on the NHWC / hoisted path.
+class _HoistSource(Function):
+    """Identity on a hoisted addend P (conv(inp, W_inp) + bias, computed once per forward).  Every GRU step consumes the
+    returned tensor, returns no gradient for it, and instead accumulates its share into `acc` inside its own backward
+    kernels (acc = on the last iteration, acc += on the others: the last iteration's backward runs first).  This node is
+    scheduled by autograd after all of them and hands `acc` on — the sum over iterations without 11 ATen adds per addend."""
+
+    @staticmethod
+    def forward(ctx, P, acc):
+        ctx.acc = acc
+        ctx.set_materialize_grads(False)
+        return P.view_as(P)
+
+    @staticmethod
+    def backward(ctx, g):
+        acc = ctx.acc
+        ctx.acc = None
+        return (acc if g is None else acc + g), None
+
+
+def hoist_sources(hoist):
+    """[(W_zr, P_zr, W_q, P_q, pad)] x 2 -> the same with P wrapped by _HoistSource, plus the accumulators."""
+    out = []
+    for (wzr, pzr, wq, pq, pad) in hoist:
+        azr, aq = torch.empty_like(pzr), torch.empty_like(pq)
+        out.append((wzr, _HoistSource.apply(pzr, azr), wq, _HoistSource.apply(pq, aq), pad, azr, aq))
+    return out
+
+
+_DGRAD_DUMMY = {}
+
+
+def _dgrad(gout, weight, in_channels, pad):
+    """Data gradient of a stride-1 convolution with frozen weights (channels-last): cuDNN dgrad, nothing else."""
+    B, _, H, W = gout.shape
+    key = (gout.device, B, in_channels, H, W)
+    dummy = _DGRAD_DUMMY.get(key)
+    if dummy is None:                                  # only its sizes / memory format are read
+        dummy = torch.empty((B, in_channels, H, W), device=gout.device, dtype=gout.dtype, memory_format=_CL)
+        _DGRAD_DUMMY[key] = dummy
+    return torch.ops.aten.convolution_backward(gout, dummy, weight, None, (1, 1), pad, (1, 1), False, (0, 0), 1,
+                                               (True, False, False))[0]
+
+
+class _GRUStepX(Function):
+    @staticmethod
+    def forward(ctx, h, m, pzr1, pq1, pzr2, pq2, wzr1, wq1, wzr2, wq2, pad1, pad2, accs, acc_mode):
+        import ctypes as C
+        import torch.nn.functional as F
+        lib, P, s = _lib.load(), _lib.ptr, _lib.stream()
+        h, m = h.contiguous(memory_format=_CL), m.contiguous(memory_format=_CL)
+        _check(h, m, pzr1, pq1, pzr2, pq2, name="gru_step_x")
+        B, Ch, H, W = h.shape
+        Cm = m.shape[1]
+        npix = B * H * W
+
+        def new(c):
+            return torch.empty((B, c, H, W), device=h.device, dtype=torch.float32, memory_format=_CL)
+        hm = new(Ch + Cm)
+        ptrs = (C.c_void_p * 2)(h.data_ptr(), m.data_ptr())
+        chans = (C.c_int * 2)(Ch, Cm)
+        _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), 2, P(hm), npix, s), "pcfa_cat_channels_last")
+        saved = []
+        hin = h
+        for (wzr, pzr, wq, pq, pad, last) in ((wzr1, pzr1, wq1, pq1, pad1, False), (wzr2, pzr2, wq2, pq2, pad2, True)):
+            zr = F.conv2d(hm, wzr, None, 1, pad)
+            z, r, rhm = new(Ch), new(Ch), new(Ch + Cm)
+            _lib.check(lib.pcfa_gru_gates_x_forward(P(zr), P(pzr), P(hin), P(m), P(z), P(r), P(rhm), Ch, Cm, npix, s), "pcfa_gru_gates_x_forward")
+            qp = F.conv2d(rhm, wq, None, 1, pad)
+            q, hn = new(Ch), new(Ch)
+            hm = None if last else new(Ch + Cm)
+            _lib.check(lib.pcfa_gru_blend_x_forward(P(z), P(qp), P(pq), P(hin), P(m), P(q), P(hn), P(hm), Ch, Cm, npix, s), "pcfa_gru_blend_x_forward")
+            saved += [z, r, q, hin]
+            hin = hn
+        ctx.save_for_backward(*saved, wzr1, wq1, wzr2, wq2)
+        ctx.pads, ctx.accs, ctx.acc_mode, ctx.cm = (pad1, pad2), accs, int(acc_mode), Cm
+        return hin
+
+    @staticmethod
+    def backward(ctx, gh2):
+        lib, P, s = _lib.load(), _lib.ptr, _lib.stream()
+        z1, r1, q1, h0, z2, r2, q2, h1, wzr1, wq1, wzr2, wq2 = ctx.saved_tensors
+        (pad1, pad2), (azr1, aq1, azr2, aq2), mode, Cm = ctx.pads, ctx.accs, ctx.acc_mode, ctx.cm
+        B, Ch, H, W = h0.shape
+        npix = B * H * W
+        gh2 = gh2.contiguous(memory_format=_CL)
+
+        def new(c):
+            return torch.empty((B, c, H, W), device=h0.device, dtype=torch.float32, memory_format=_CL)
+        # ---- vertical half step (second)
+        gz, gq, gh1_a = new(Ch), new(Ch), new(Ch)
+        _lib.check(lib.pcfa_gru_blend_x_backward_acc(P(z2), P(q2), P(h1), P(gh2), None, None, P(gz), P(gq), P(gh1_a), P(aq2), mode,
+                                                     Ch, Cm, npix, s), "pcfa_gru_blend_x_backward_acc")
+        grhm2 = _dgrad(gq, wq2, Ch + Cm, pad2)
+        gzr, gh1_b = new(2 * Ch), new(Ch)
+        _lib.check(lib.pcfa_gru_gates_x_backward_acc(P(z2), P(r2), P(h1), P(gz), P(grhm2), P(gzr), P(gh1_b), P(azr2), mode, Ch, Cm, npix, s),
+                   "pcfa_gru_gates_x_backward_acc")
+        ghm2 = _dgrad(gzr, wzr2, Ch + Cm, pad2)
+        # ---- horizontal half step (first): grad of h1 = gh1_a + gh1_b + ghm2[:, :C]
+        gz, gq, gh0_a = new(Ch), new(Ch), new(Ch)
+        _lib.check(lib.pcfa_gru_blend_x_backward_acc(P(z1), P(q1), P(h0), P(gh1_a), P(gh1_b), P(ghm2), P(gz), P(gq), P(gh0_a), P(aq1), mode,
+                                                     Ch, Cm, npix, s), "pcfa_gru_blend_x_backward_acc")
+        grhm1 = _dgrad(gq, wq1, Ch + Cm, pad1)
+        gzr, gh0_b = new(2 * Ch), new(Ch)
+        _lib.check(lib.pcfa_gru_gates_x_backward_acc(P(z1), P(r1), P(h0), P(gz), P(grhm1), P(gzr), P(gh0_b), P(azr1), mode, Ch, Cm, npix, s),
+                   "pcfa_gru_gates_x_backward_acc")
+        ghm1 = _dgrad(gzr, wzr1, Ch + Cm, pad1)
+        gh, gm = new(Ch), new(Cm)
+        _lib.check(lib.pcfa_gru_step_combine(P(gh0_a), P(gh0_b), P(ghm1), P(grhm1), P(grhm2), P(ghm2), P(gh), P(gm), Ch, Cm, npix, s),
+                   "pcfa_gru_step_combine")
+        ctx.accs = None
+        return (gh, gm) + (None,) * 12
+
+
+def gru_step_x(h, m, sources, last_iteration: bool):
+    """h' = SepConvGRU(h, [inp | m]) on the hoisted NHWC path as ONE autograd node; `sources` from hoist_sources()."""
+    (wzr1, pzr1, wq1, pq1, pad1, azr1, aq1), (wzr2, pzr2, wq2, pq2, pad2, azr2, aq2) = sources
+    return _GRUStepX.apply(h, m, pzr1, pq1, pzr2, pq2, wzr1, wq1, wzr2, wq2, tuple(pad1), tuple(pad2), (azr1, aq1, azr2, aq2),
+                           1 if last_iteration else 2)

@@ -17,6 +17,8 @@ nothing else (raft.py:141-142) — outputs and gradients are unchanged.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -345,12 +347,15 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(256, 64 * 9, 1))
 
-    def forward(self, net, inp, corr, flow, want_mask=True, cl=False, hoist=None, raw_mask=False):
+    def forward(self, net, inp, corr, flow, want_mask=True, cl=False, hoist=None, raw_mask=False, step_sources=None, last=False):
         """cl=True: every tensor is torch.channels_last (cuDNN's sm_100 kernels are NHWC-only; with NCHW activations
         it converts around every convolution: 3 ms of the 11.8 ms RAFT closure)."""
         from ..gru_ops import cat_channels
         motion = self.encoder(flow, corr, cl)
-        if hoist is not None:
+        if step_sources is not None:                      # one autograd node for the whole GRU step (gru_ops.gru_step_x)
+            from ..gru_ops import gru_step_x
+            net = gru_step_x(net, motion, step_sources, last)
+        elif hoist is not None:
             net = self.gru.forward_x(net, motion, hoist)
         else:
             net = self.gru(net, cat_channels([inp, motion], cl), cl)
@@ -455,13 +460,16 @@ class RAFT(nn.Module):
         from ..corr_block import CorrBlock as _OwnCorrBlock
         cl = (bool(getattr(self.update_block, "channels_last", False)) and dev_type == "cuda" and not amp
               and isinstance(corr_fn, _OwnCorrBlock) and isinstance(self.update_block, BasicUpdateBlock))
-        hoist = None
+        hoist = step_sources = None
         if cl:
             net = net.contiguous(memory_format=torch.channels_last)
             inp = inp.contiguous(memory_format=torch.channels_last)
             frozen = not any(p.requires_grad for p in self.update_block.gru.parameters())
             if frozen and net.shape[1] % 4 == 0 and inp.shape[1] % 4 == 0:
                 hoist = self.update_block.gru.hoisted(inp)
+                if torch.is_grad_enabled() and os.environ.get("PCFA_GRU_STEP", "1") != "0":
+                    from ..gru_ops import hoist_sources
+                    step_sources = hoist_sources(hoist)
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
@@ -470,7 +478,8 @@ class RAFT(nn.Module):
             with torch.autocast(dev_type, enabled=amp):
                 if cl:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow.contiguous(memory_format=torch.channels_last),
-                                                                 want_mask=need_up, cl=True, hoist=hoist, raw_mask=True)
+                                                                 want_mask=need_up, cl=True, hoist=hoist, raw_mask=True,
+                                                                 step_sources=step_sources, last=itr == iters - 1)
                     delta_flow = delta_flow.contiguous()
                 else:
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
