@@ -375,6 +375,19 @@ int pcfa_softmax_rows_f16_backward(const void* attn, const void* grad_attn, void
  *                           d <- -H*grad;  scalars_out = { <grad,d>, max|d| }.  One cooperative launch.
  * workspace: pcfa_lbfgs_workspace_bytes(). */
 int64_t pcfa_lbfgs_workspace_bytes(void);
+/* One host round trip per iteration (the f-1 criterion): the history bookkeeping and torch's pre-update break test live on
+ * the device.
+ *   pcfa_lbfgs_update_history : <y,s>, <y,y> of the candidate pair; if <y,s> > 1e-10 it replaces the oldest / next free
+ *                               ring slot, ro[slot] = 1/<y,s>, *h_diag = <y,s>/<y,y>; ring_out = new {start, num_old}
+ *                               (ring_in != ring_out, both int[2] on the device); always grad_prev <- grad.
+ *   pcfa_lbfgs_direction_step : two-loop recursion over ring = {start, num_old}, then param += t*d unless
+ *                               <grad,d> > -tol_change; scalars_out = { <grad,d>, max|d| }. */
+int pcfa_lbfgs_update_history(const float* grad, float* grad_prev, const float* d, float t, float* S, float* Y, float* ro,
+                              float* h_diag, const int* ring_in, int* ring_out, float* scalars_out, void* workspace, int64_t n,
+                              int history_capacity, pcfa_stream_t stream);
+int pcfa_lbfgs_direction_step(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag, float* d,
+                              const int* ring, float* param, float t, float tol_change, float* scalars_out, void* workspace,
+                              int64_t n, int history_capacity, pcfa_stream_t stream);
 int pcfa_lbfgs_store_pair(const float* grad, float* grad_prev, const float* d, float t, float* s_slot, float* y_slot,
                           float* scalars_out, void* workspace, int64_t n, pcfa_stream_t stream);
 int pcfa_lbfgs_direction(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag, float* d,

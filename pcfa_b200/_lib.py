@@ -73,6 +73,8 @@ SIGNATURES = {
     "pcfa_gru_blend_x_backward_acc": (c_i, [c_fp] * 10 + [c_i, c_i, c_i, c_i64, c_fp]),
     "pcfa_gru_step_combine": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
     "pcfa_lbfgs_workspace_bytes": (c_i64, []),
+    "pcfa_lbfgs_update_history": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
+    "pcfa_lbfgs_direction_step": (c_i, [c_fp] * 6 + [c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_lbfgs_store_pair": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_lbfgs_direction": (c_i, [c_fp] * 8 + [c_i64, c_i, c_i, c_i, c_fp]),
     "pcfa_cat_channels_last": (c_i, [c_fp, c_fp, c_i, c_fp, c_i64, c_fp]),

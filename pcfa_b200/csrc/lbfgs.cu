@@ -42,8 +42,10 @@ __device__ __forceinline__ float lb_block_sum(float v, float* sh) {
 __global__ void __launch_bounds__(LB_THREADS)
 lbfgs_two_loop_kernel(const float* __restrict__ S, const float* __restrict__ Y, const float* __restrict__ ro,
                       const float* __restrict__ g, const float* __restrict__ hdiag, float* __restrict__ d,
-                      float* __restrict__ partials, float* __restrict__ scalars, int64_t n, int m, int start, int num_old) {
+                      float* __restrict__ partials, float* __restrict__ scalars, int64_t n, int m, int start, int num_old,
+                      const int* __restrict__ ring, float* __restrict__ param, float t, float tol_change) {
     cg::grid_group grid = cg::this_grid();
+    if (ring) { start = ring[0]; num_old = ring[1]; }      // history bookkeeping kept on the device (lbfgs_pair_commit_kernel)
     __shared__ float sh[LB_THREADS / 32];
     __shared__ float al[LB_MAX_HISTORY];
     const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
@@ -90,6 +92,10 @@ lbfgs_two_loop_kernel(const float* __restrict__ S, const float* __restrict__ Y, 
     float gd = 0.f, mx = 0.f;
     for (int64_t i = lo + threadIdx.x; i < hi; i += LB_THREADS) { const float v = d[i]; gd = fmaf(__ldg(g + i), v, gd); mx = fmaxf(mx, fabsf(v)); }
     const float gtd = total(lb_block_sum(gd, sh));
+    // torch: `if gtd > -tolerance_change: break` BEFORE the parameter update — here a device-side predicate, identical in
+    // every CTA (same ordered sum), so the host needs no round trip between the direction and the update
+    if (param && !(gtd > -tol_change))
+        for (int64_t i = lo + threadIdx.x; i < hi; i += LB_THREADS) param[i] = fmaf(t, d[i], param[i]);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
     __syncthreads();
@@ -122,6 +128,50 @@ lbfgs_pair_kernel(const float* __restrict__ g, float* __restrict__ g_prev, const
     ys = lb_block_sum(ys, sh);
     yy = lb_block_sum(yy, sh);
     if (threadIdx.x == 0) { partials[blockIdx.x] = ys; partials[gridDim.x + blockIdx.x] = yy; }
+}
+
+// <y,s>, <y,y> of the candidate pair WITHOUT writing it (the slot it would take may still hold live history)
+__global__ void __launch_bounds__(LB_THREADS)
+lbfgs_pair_reduce_kernel(const float* __restrict__ g, const float* __restrict__ g_prev, const float* __restrict__ d, float t,
+                         float* __restrict__ partials, int64_t n) {
+    __shared__ float sh[LB_THREADS / 32];
+    float ys = 0.f, yy = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * LB_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LB_THREADS) {
+        const float y = g[i] - g_prev[i], s = t * d[i];
+        ys = fmaf(y, s, ys); yy = fmaf(y, y, yy);
+    }
+    ys = lb_block_sum(ys, sh);
+    yy = lb_block_sum(yy, sh);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = ys; partials[gridDim.x + blockIdx.x] = yy; }
+}
+
+// torch/optim/lbfgs.py: `if ys > 1e-10:` pop the oldest pair when the history is full, append (y, s), ro, H_diag = ys / yy.
+// Decided on the device from the reduced scalars; ring = {start, num_old} is double-buffered (ring_in read by every
+// thread, ring_out written by one) so that the launch needs no grid barrier.  Always: g_prev <- g.
+__global__ void __launch_bounds__(LB_THREADS)
+lbfgs_pair_commit_kernel(const float* __restrict__ g, float* __restrict__ g_prev, const float* __restrict__ d, float t,
+                         float* __restrict__ S, float* __restrict__ Y, float* __restrict__ ro, float* __restrict__ hdiag,
+                         const int* __restrict__ ring_in, int* __restrict__ ring_out, const float* __restrict__ scalars,
+                         int64_t n, int m) {
+    const float ys = scalars[0], yy = scalars[1];
+    const int start = ring_in[0], num_old = ring_in[1];
+    const bool accept = ys > 1e-10f;
+    const int slot = num_old < m ? (start + num_old) % m : start;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (accept) {
+            ring_out[0] = num_old < m ? start : (start + 1) % m;
+            ring_out[1] = num_old < m ? num_old + 1 : m;
+            ro[slot] = 1.0f / ys;
+            *hdiag = ys / yy;
+        } else { ring_out[0] = start; ring_out[1] = num_old; }
+    }
+    float* s_out = S + (int64_t)slot * n;
+    float* y_out = Y + (int64_t)slot * n;
+    for (int64_t i = (int64_t)blockIdx.x * LB_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LB_THREADS) {
+        const float gi = g[i];
+        if (accept) { y_out[i] = gi - g_prev[i]; s_out[i] = t * d[i]; }
+        g_prev[i] = gi;
+    }
 }
 
 __global__ void lbfgs_pair_finalize_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
@@ -178,8 +228,65 @@ extern "C" int pcfa_lbfgs_direction(const float* S, const float* Y, const float*
     int64_t want = (n + 4 * LB_THREADS - 1) / (4 * LB_THREADS);
     int grid = (int)(want < max_ctas ? (want < 1 ? 1 : want) : max_ctas);
     float* part = reinterpret_cast<float*>(workspace);
+    const int* ring = nullptr; float* param = nullptr; float t = 0.f, tol = 0.f;
     void* args[] = {(void*)&S, (void*)&Y, (void*)&ro, (void*)&grad, (void*)&h_diag, (void*)&d, (void*)&part, (void*)&scalars_out,
-                    (void*)&n, (void*)&history_capacity, (void*)&start, (void*)&num_old};
+                    (void*)&n, (void*)&history_capacity, (void*)&start, (void*)&num_old, (void*)&ring, (void*)&param, (void*)&t, (void*)&tol};
+    PCFA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lbfgs_two_loop_kernel, dim3(grid), dim3(LB_THREADS), args, 0, as_stream(stream)));
+    return after_launch();
+}
+
+static int lb_coop_grid(int64_t n, int* grid_out) {
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        PCFA_CUDA_TRY(cudaGetDevice(&dev));
+        PCFA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PCFA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbfgs_two_loop_kernel, LB_THREADS, 0));
+        max_ctas = sms * (per_sm > 2 ? 2 : per_sm);
+        if (max_ctas > LB_MAX_CTAS) max_ctas = LB_MAX_CTAS;
+        if (max_ctas < 1) return PCFA_E_NODEVICE;
+    }
+    const int64_t want = (n + 4 * LB_THREADS - 1) / (4 * LB_THREADS);
+    *grid_out = (int)(want < max_ctas ? (want < 1 ? 1 : want) : max_ctas);
+    return PCFA_OK;
+}
+
+// History update decided on the device: scalars_out = {<y,s>, <y,y>}; ring_in / ring_out: int[2] = {start, num_old}.
+extern "C" int pcfa_lbfgs_update_history(const float* grad, float* grad_prev, const float* d, float t, float* S, float* Y, float* ro,
+                                         float* h_diag, const int* ring_in, int* ring_out, float* scalars_out, void* workspace,
+                                         int64_t n, int history_capacity, pcfa_stream_t stream) {
+    if (!grad || !grad_prev || !d || !S || !Y || !ro || !h_diag || !ring_in || !ring_out || ring_in == ring_out || !scalars_out ||
+        !workspace || n <= 0 || history_capacity <= 0 || history_capacity > LB_MAX_HISTORY)
+        return PCFA_E_BADARG;
+    int64_t blocks = (n + LB_THREADS - 1) / LB_THREADS;
+    const int64_t cap = (int64_t)kNumSMs * 4;
+    if (blocks > cap) blocks = cap;
+    float* part = reinterpret_cast<float*>(workspace);
+    cudaStream_t s = as_stream(stream);
+    lbfgs_pair_reduce_kernel<<<(int)blocks, LB_THREADS, 0, s>>>(grad, grad_prev, d, t, part, n);
+    PCFA_TRY(after_launch());
+    lbfgs_pair_finalize_kernel<<<1, 256, 0, s>>>(part, (int)blocks, scalars_out);
+    PCFA_TRY(after_launch());
+    lbfgs_pair_commit_kernel<<<(int)blocks, LB_THREADS, 0, s>>>(grad, grad_prev, d, t, S, Y, ro, h_diag, ring_in, ring_out, scalars_out,
+                                                               n, history_capacity);
+    return after_launch();
+}
+
+// Two-loop recursion over the device-side ring, then param += t * d unless <grad, d> > -tol_change (torch's break, as a
+// device predicate).  scalars_out = {<grad, d>, max |d|}.
+extern "C" int pcfa_lbfgs_direction_step(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag,
+                                         float* d, const int* ring, float* param, float t, float tol_change, float* scalars_out,
+                                         void* workspace, int64_t n, int history_capacity, pcfa_stream_t stream) {
+    if (!S || !Y || !ro || !grad || !h_diag || !d || !ring || !param || !scalars_out || !workspace || n <= 0 ||
+        history_capacity <= 0 || history_capacity > LB_MAX_HISTORY)
+        return PCFA_E_BADARG;
+    int grid = 0;
+    PCFA_TRY(lb_coop_grid(n, &grid));
+    float* part = reinterpret_cast<float*>(workspace);
+    int start = 0, num_old = 0;
+    void* args[] = {(void*)&S, (void*)&Y, (void*)&ro, (void*)&grad, (void*)&h_diag, (void*)&d, (void*)&part, (void*)&scalars_out,
+                    (void*)&n, (void*)&history_capacity, (void*)&start, (void*)&num_old, (void*)&ring, (void*)&param, (void*)&t,
+                    (void*)&tol_change};
     PCFA_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)lbfgs_two_loop_kernel, dim3(grid), dim3(LB_THREADS), args, 0, as_stream(stream)));
     return after_launch();
 }

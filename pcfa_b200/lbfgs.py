@@ -3,12 +3,12 @@
 `DeviceLBFGS` follows torch.optim.LBFGS.step (torch/optim/lbfgs.py — the optimiser the reference constructs at
 attack_PCFA.py:97,114 with max_iter=10 and defaults lr=1, max_eval=12, tolerance_grad=1e-7, tolerance_change=1e-9,
 history_size=100, no line search) decision for decision, but keeps the parameters, the gradient and the (s, y)
-history in flat device buffers and runs the vector algebra in three launches per iteration instead of ~4*history:
-    pcfa_lbfgs_store_pair  (y, s into the ring buffers, <y,s>, <y,y>)
-    pcfa_lbfgs_direction   (two-loop recursion, <g,d>, max|d|: one cooperative launch)
-    flat_param += t * d
-Host round trips per iteration: two small D2H reads (the curvature test and the stopping tests need the same scalars
-torch's implementation syncs on, one by one)."""
+history in flat device buffers and runs the vector algebra in four launches per iteration instead of ~4*history:
+    pcfa_lbfgs_update_history  (<y,s>, <y,y>; curvature test, ring-buffer update, ro, H_diag decided on the device)
+    pcfa_lbfgs_direction_step  (two-loop recursion, <g,d>, max|d|, then param += t*d unless <g,d> > -tolerance_change:
+                                one cooperative launch)
+Host round trips: ONE small D2H read per inner iteration, after its closure (the stopping tests torch syncs on one by
+one, packed), none on the last iteration of a step."""
 from __future__ import annotations
 
 import torch
@@ -36,23 +36,21 @@ class DeviceLBFGS:
         self.hdiag = torch.ones(1, device=dev)
         self.d = torch.empty(n, device=dev)
         self.g_prev = torch.empty(n, device=dev)
-        self.sc = torch.zeros(4, device=dev)
+        self.sc = torch.zeros(4, device=dev)                     # {<y,s>, <y,y>, <g,d>, max|d|}
+        self.ring = torch.zeros(2, 2, dtype=torch.int32, device=dev)   # double-buffered {start, num_old}
+        self.cur = 0
         lib = _lib.load()
         self.ws = torch.empty(lib.pcfa_lbfgs_workspace_bytes(), device=dev, dtype=torch.uint8)
-        self.state = dict(func_evals=0, n_iter=0, t=None, start=0, num_old=0, prev_loss=None, have_prev=False)
-
-    # history slot that the next pair goes to, ring semantics of old_dirs.pop(0)/append
-    def _push_slot(self):
-        st = self.state
-        if st["num_old"] < self.m:
-            slot = (st["start"] + st["num_old"]) % self.m
-            st["num_old"] += 1
-        else:
-            slot = st["start"]
-            st["start"] = (st["start"] + 1) % self.m
-        return slot
+        self.state = dict(func_evals=0, n_iter=0, t=None, prev_loss=None)
 
     def step(self, closure):
+        """torch.optim.LBFGS.step (no line search) with ONE host round trip per inner iteration: after each closure the
+        host reads one packed block {loss, max|g|, <y,s>, <y,y>, <g,d>, max|d|}; the history bookkeeping
+        (pcfa_lbfgs_update_history) and the pre-update break test (pcfa_lbfgs_direction_step) are device-side predicates.
+        The very first iteration of the optimiser's life (d = -g, t = min(1, 1/|g|_1)) keeps its extra reads.
+        One mechanical difference: when `<g,d> > -tolerance_change` fires (torch breaks before the update), the update is
+        skipped on the device but the closure of that iteration has already been launched; it re-evaluates the unchanged
+        point, is not counted in func_evals, and changes neither the parameters nor the history."""
         lib, st, s = _lib.load(), self.state, _lib.stream()
         P = _lib.ptr
         orig_loss = closure()
@@ -66,56 +64,48 @@ class DeviceLBFGS:
         while n_iter < self.max_iter:
             n_iter += 1
             st["n_iter"] += 1
-            if st["n_iter"] == 1:
+            first = st["n_iter"] == 1
+            if first:
                 torch.neg(self.g, out=self.d)
-                st["start"], st["num_old"] = 0, 0
+                self.ring[0].zero_()
+                self.cur = 0
                 self.hdiag.fill_(1.0)
+                self.g_prev.copy_(self.g)
                 gtd = -float(self.g.dot(self.g))
-                dmax = None
+                t = min(1.0, 1.0 / float(self.g.abs().sum())) * self.lr
+                if gtd > -self.tolerance_change:
+                    prev_loss = loss
+                    break
+                self.p.add_(self.d, alpha=t)
             else:
                 if self.S is None:
                     self.S = torch.empty(self.m, self.n, device=self.p.device)
                     self.Y = torch.empty(self.m, self.n, device=self.p.device)
-                # candidate pair into the slot it would occupy; the ring only advances if <y,s> > 1e-10 (lbfgs.py)
-                cand = (st["start"] + st["num_old"]) % self.m if st["num_old"] < self.m else st["start"]
-                if st["num_old"] == self.m:
-                    # the slot to be overwritten still belongs to the history if the pair is rejected: stage in d-sized scratch
-                    s_slot, y_slot = self._scratch()
-                else:
-                    s_slot, y_slot = self.S[cand], self.Y[cand]
-                _lib.check(lib.pcfa_lbfgs_store_pair(P(self.g), P(self.g_prev), P(self.d), float(t), P(s_slot), P(y_slot), P(self.sc),
-                                                     P(self.ws), self.n, s), "pcfa_lbfgs_store_pair")
-                ys, yy = self.sc[:2].tolist()
-                if ys > 1e-10:
-                    slot = self._push_slot()
-                    if s_slot.data_ptr() != self.S[slot].data_ptr():
-                        self.S[slot].copy_(s_slot); self.Y[slot].copy_(y_slot)
-                    self.ro[slot] = 1.0 / ys
-                    self.hdiag.fill_(ys / yy)
-                _lib.check(lib.pcfa_lbfgs_direction(P(self.S), P(self.Y), P(self.ro), P(self.g), P(self.hdiag), P(self.d), P(self.sc[2:]),
-                                                    P(self.ws), self.n, self.m, st["start"], st["num_old"], s), "pcfa_lbfgs_direction")
-                gtd, dmax = self.sc[2:4].tolist()
-            if not st["have_prev"] or st["n_iter"] == 1:
-                self.g_prev.copy_(self.g)
-                st["have_prev"] = True
-            prev_loss = loss
-            if st["n_iter"] == 1:
-                t = min(1.0, 1.0 / float(self.g.abs().sum())) * self.lr
-            else:
+                ring_in, ring_out = self.ring[self.cur], self.ring[self.cur ^ 1]
+                _lib.check(lib.pcfa_lbfgs_update_history(P(self.g), P(self.g_prev), P(self.d), float(t), P(self.S), P(self.Y), P(self.ro),
+                                                         P(self.hdiag), P(ring_in), P(ring_out), P(self.sc), P(self.ws), self.n, self.m, s),
+                           "pcfa_lbfgs_update_history")
+                self.cur ^= 1
                 t = self.lr
-            if gtd > -self.tolerance_change:
-                break
-            self.p.add_(self.d, alpha=t)
-            ls_func_evals = 0
-            if n_iter != self.max_iter:
-                with torch.enable_grad():
-                    l = closure()
-                loss, gmax = torch.stack([l.detach().reshape(()), self.g.abs().max()]).tolist()
-                ls_func_evals = 1
-            current_evals += ls_func_evals
-            st["func_evals"] += ls_func_evals
+                _lib.check(lib.pcfa_lbfgs_direction_step(P(self.S), P(self.Y), P(self.ro), P(self.g), P(self.hdiag), P(self.d), P(ring_out),
+                                                         P(self.p), float(t), float(self.tolerance_change), P(self.sc[2:]), P(self.ws),
+                                                         self.n, self.m, s), "pcfa_lbfgs_direction_step")
+            prev_loss = loss
             if n_iter == self.max_iter:
-                break
+                break                                         # torch evaluates no closure on the last iteration: no read-back either
+            with torch.enable_grad():
+                l = closure()
+            vals = torch.cat([torch.stack([l.detach().reshape(()).float(), self.g.abs().max()]), self.sc]).tolist()
+            new_loss, gmax = vals[0], vals[1]
+            if not first:
+                gtd, dmax = vals[4], vals[5]
+                if gtd > -self.tolerance_change:              # the update was skipped on the device: torch's pre-update break
+                    break
+            else:
+                dmax = None
+            loss = new_loss
+            current_evals += 1
+            st["func_evals"] += 1
             if current_evals >= self.max_eval:
                 break
             if gmax <= self.tolerance_grad:
@@ -129,7 +119,8 @@ class DeviceLBFGS:
         st["t"], st["prev_loss"] = t, prev_loss
         return orig_loss
 
-    def _scratch(self):
-        if not hasattr(self, "_scr"):
-            self._scr = torch.empty(2, self.n, device=self.p.device)
-        return self._scr[0], self._scr[1]
+    @property
+    def history(self):
+        """(start, num_old) of the device-side ring (one D2H read; diagnostics and tests only)."""
+        a = self.ring[self.cur].tolist()
+        return a[0], a[1]

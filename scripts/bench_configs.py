@@ -14,7 +14,7 @@ from pcfa_b200.networks.weights import synthetic_pair
 _lib.load()
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
-only = sys.argv[1:] or ["RAFT", "GMA", "PWCNet", "FlowNet2", "RAFT-universal8"]
+only = sys.argv[1:] or ["RAFT", "GMA", "GMA-batch8", "PWCNet", "FlowNet2", "RAFT-universal8"]
 rows = []
 
 
@@ -51,6 +51,20 @@ for name in only:
             t4, n4 = min((run(4) for _ in range(2)), key=lambda r: r[0])
             row.update(outer_step_s=(t4 - t1) / 3, closures_per_outer_step=(n4 - n1) / 3,
                        ms_per_closure_incl_host=1e3 * (t4 - t1) / max(1, n4 - n1), pairs=8)
+        elif name.endswith("batch8"):
+            # BASELINE config 3 at N = 1: the eight Sintel-shaped pairs of the batch evaluated as ONE batched joint closure
+            # (per-pair delta, clipping); closure time only
+            pairs = [synthetic_pair(i, H, W) for i in range(8)]
+            a = torch.cat([p[0] for p in pairs]).to(dev) / 255.; b = torch.cat([p[1] for p in pairs]).to(dev) / 255.
+            padder, (a, b) = preprocess_img(net_name, a, b)
+            a, b = a.contiguous(), b.contiguous()
+            fo = J.FusedObjective(_net_forward(model, net_name, None), a, b, torch.zeros(8, 2, H, W, device=dev), mode=J.box_mode("clipping", joint=True),
+                                  joint=True, pad=padder.top_left, eps_box=1e-7, scale=255.0, delta_bound=0.005,
+                                  mu=resolve_mu(-1., 0.005, "zero"), loss="aee")
+            ev = GraphedEvaluate(fo, torch.zeros_like(a), None, use_graph=True)
+            row.update(closure_ms=closure_ms(ev, n=10, warm=3), pairs=8)
+            row["ms_per_pair"] = row["closure_ms"] / 8
+            del ev, fo
         else:
             i1, i2 = synthetic_pair(0, H, W)
             i1, i2 = i1.to(dev), i2.to(dev)
@@ -87,6 +101,7 @@ for name in only:
     except Exception as e:                                           # keep going: one config must not hide the others
         row["error"] = repr(e)[:300]
     row["max_mem_GB"] = round(torch.cuda.max_memory_allocated() / 2**30, 2)
+    row["max_reserved_GB"] = round(torch.cuda.max_memory_reserved() / 2**30, 2)
     torch.cuda.reset_peak_memory_stats()
     print(row, flush=True)
     rows.append(row)
