@@ -76,3 +76,23 @@ def test_no_cpu_fallback_on_cpu_tensors():
         CorrBlock(x, x)
     with pytest.raises(RuntimeError, match="no CPU path"):
         ChannelNorm()(x)
+
+
+def test_reference_binding_bodies_compile_against_the_header():
+    """INTEGRATION.md section B is kept as compilable code (integration/reference_bindings.cpp): the bodies a maintainer
+    would put into the reference's pybind11 modules.  Syntax-checked (g++ -fsyntax-only) against the torch headers and
+    include/pcfa_b200.h, so the documented boundary cannot drift from the C ABI."""
+    import shutil
+    import subprocess
+    import sysconfig
+    from pathlib import Path
+    from torch.utils import cpp_extension
+    root = Path(__file__).resolve().parents[1]
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else shutil.which("g++")
+    cuda_inc = Path("/usr/local/cuda/include")
+    if cxx is None or not cuda_inc.exists():
+        pytest.skip("no host compiler / CUDA headers")
+    inc = cpp_extension.include_paths() + [str(cuda_inc), str(root / "include"), sysconfig.get_paths()["include"]]
+    cmd = [cxx, "-std=c++17", "-fsyntax-only"] + [f"-I{p}" for p in inc] + [str(root / "integration" / "reference_bindings.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-4000:]
