@@ -108,7 +108,12 @@ class GMAUpdateBlock(nn.Module):
         motion_global = self.aggregator(attention, motion)
         net = self.gru(net, torch.cat([inp, motion, motion_global], dim=1))
         delta_flow = self.flow_head(net)
-        mask = (self.mask(net) if raw_mask else 0.25 * self.mask(net)) if want_mask else None
+        mask = None
+        if want_mask:
+            from ..conv_ops import conv_act
+            mask = conv_act(self.mask[2], conv_act(self.mask[0], net, True), False)
+            if not raw_mask:
+                mask = 0.25 * mask
         return net, mask, delta_flow
 
 

@@ -78,11 +78,15 @@ def _conv_norm_act(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool
     if (x.is_cuda and isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats and frozen
             and conv.padding_mode == "zeros"):
         w, b = _bn_folded(conv, norm)
+        from ..conv_ops import conv_act                     # bias + ReLU as the convolution's fused epilogue (csrc/bias_act.cu)
+        return conv_act(conv, x, relu, w, b, "_pcfa_bn_fold16")
+    if (x.is_cuda and frozen and isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats
+            and conv.padding_mode == "zeros" and conv.bias is not None):
+        # a per-channel constant is removed by the instance norm that follows: skip the bias add (a broadcasting ATen
+        # launch over up to 58 MB) — (conv + b) - mean(conv + b) == conv - mean(conv)
         from .amp import amp_half_active, half_params
-        if amp_half_active(x):                                # frozen weights: autocast would re-cast them on every call
-            w, b = half_params(conv, w, b, "_pcfa_bn_fold16")
-        y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
-        return F.relu(y) if relu else y
+        w = half_params(conv, conv.weight, None, "_pcfa_w16_nobias")[0] if amp_half_active(x) else conv.weight
+        return _norm_act(norm, F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups), relu)
     return _norm_act(norm, conv(x), relu)
 
 
@@ -207,7 +211,8 @@ class FlowHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.conv2(self.relu(self.conv1(x)))
+        from ..conv_ops import conv_act
+        return conv_act(self.conv2, conv_act(self.conv1, x, True), False)
 
 
 def _zr_weights(cz: nn.Conv2d, cr: nn.Conv2d):
@@ -316,9 +321,10 @@ class BasicMotionEncoder(nn.Module):
 
     def forward(self, flow, corr, cl=False):
         from ..gru_ops import cat_channels
-        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
-        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
-        out = F.relu(self.conv(cat_channels([cor, flo], cl)))
+        from ..conv_ops import conv_act
+        cor = conv_act(self.convc2, conv_act(self.convc1, corr, True), True)
+        flo = conv_act(self.convf2, conv_act(self.convf1, flow, True), True)
+        out = conv_act(self.conv, cat_channels([cor, flo], cl), True)
         return cat_channels([out, flow], cl)
 
 
@@ -361,7 +367,12 @@ class BasicUpdateBlock(nn.Module):
             net = self.gru(net, cat_channels([inp, motion], cl), cl)
         delta_flow = self.flow_head(net)
         # .25 "to balance gradients" (update.py:135); raw_mask=True leaves it to the fused up-sampling kernel's mask_scale
-        mask = (self.mask(net) if raw_mask else 0.25 * self.mask(net)) if want_mask else None
+        mask = None
+        if want_mask:
+            from ..conv_ops import conv_act
+            mask = conv_act(self.mask[2], conv_act(self.mask[0], net, True), False)
+            if not raw_mask:
+                mask = 0.25 * mask
         return net, mask, delta_flow
 
 

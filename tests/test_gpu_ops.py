@@ -489,3 +489,32 @@ def test_softmax_rows_f16_matches_fp32_softmax_of_the_fp16_input(rows, cols):
     got = sim.grad.float()
     scale = float(want.abs().max()) + 1e-30
     assert float((got - want).abs().max()) <= 2e-3 * scale
+
+
+# ----------------------------------------------------------------------------------- convolution epilogue (f-4 glue)
+@pytest.mark.parametrize("cl", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("cin,cout,k,stride", [(16, 32, 3, 1), (324, 256, 1, 1), (8, 2, 3, 1), (3, 64, 7, 2)])
+def test_conv_act_matches_conv_bias_relu(cl, dtype, cin, cout, k, stride):
+    """conv_act (bias-free cuDNN convolution + fused bias/ReLU epilogue, one autograd node) against F.relu(conv(x))."""
+    from pcfa_b200.conv_ops import conv_act
+    g = torch.Generator().manual_seed(cin * cout + k)
+    conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2).cuda().to(dtype)
+    for p in conv.parameters():
+        p.requires_grad = False
+    x = torch.randn(2, cin, 20, 24, generator=g).cuda().to(dtype)
+    if cl:
+        conv = conv.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    for relu in (True, False):
+        a = x.clone().requires_grad_(True)
+        b = x.clone().requires_grad_(True)
+        y = conv_act(conv, a, relu)
+        ref = conv(b)
+        ref = torch.relu(ref) if relu else ref
+        tol = dict(rtol=1e-3, atol_rms=1e-3) if dtype == torch.float32 else dict(rtol=1e-2, atol_rms=1e-2)
+        assert_close(npy(y), npy(ref), what="conv_act fwd", **tol)
+        go = torch.randn(ref.shape, generator=g).cuda().to(dtype)
+        (y * go).sum().backward()
+        (ref * go).sum().backward()
+        assert_close(npy(a.grad), npy(b.grad), what="conv_act grad", **tol)
