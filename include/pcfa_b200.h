@@ -366,12 +366,14 @@ int pcfa_softmax_rows_f16_backward(const void* attn, const void* grad_attn, void
                                    pcfa_stream_t stream);
 
 /* --------------------------------------------------------------------------- convolution epilogue (row f-4, glue)
- * y = relu?(x + bias[c]) in place on the output of a bias-free cuDNN convolution, and the ReLU mask of the backward
+ * y = act?(x + bias[c]) in place on the output of a bias-free cuDNN convolution (act = max(v, slope*v): ReLU for slope 0,
+ * LeakyReLU otherwise; 0 <= slope < 1), and the activation mask of the backward (y > 0 ? g : slope*g)
  * (torch runs the bias as a broadcasting ATen add and the ReLU as a clamp: two launches per convolution).
  * dtype 0 = fp32, 1 = fp16.  Layout by `inner`: 1 = channels-last ([..., C] innermost; C % 4 (8 for fp16) == 0),
  * H*W = NCHW (inner % 4 (8) == 0).  n % 4 (8) == 0; pointers 16-byte aligned; otherwise PCFA_E_BADARG (caller falls back). */
-int pcfa_bias_act_forward(void* x, const void* bias, int64_t n, int C, int64_t inner, int relu, int dtype, pcfa_stream_t stream);
-int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int64_t n, int dtype, pcfa_stream_t stream);
+int pcfa_bias_act_forward(void* x, const void* bias, int64_t n, int C, int64_t inner, int relu, float slope, int dtype,
+                          pcfa_stream_t stream);
+int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int64_t n, float slope, int dtype, pcfa_stream_t stream);
 
 /* --------------------------------------------------------------------------- on-device L-BFGS
  * The vector algebra of torch.optim.LBFGS.step (torch/optim/lbfgs.py; the reference's optimiser, attack_PCFA.py:97,114)

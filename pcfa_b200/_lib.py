@@ -72,8 +72,8 @@ SIGNATURES = {
     "pcfa_gru_gates_x_backward_acc": (c_i, [c_fp] * 8 + [c_i, c_i, c_i, c_i64, c_fp]),
     "pcfa_gru_blend_x_backward_acc": (c_i, [c_fp] * 10 + [c_i, c_i, c_i, c_i64, c_fp]),
     "pcfa_gru_step_combine": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
-    "pcfa_bias_act_forward": (c_i, [c_fp, c_fp, c_i64, c_i, c_i64, c_i, c_i, c_fp]),
-    "pcfa_relu_mask_backward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
+    "pcfa_bias_act_forward": (c_i, [c_fp, c_fp, c_i64, c_i, c_i64, c_i, c_f, c_i, c_fp]),
+    "pcfa_relu_mask_backward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_f, c_i, c_fp]),
     "pcfa_lbfgs_workspace_bytes": (c_i64, []),
     "pcfa_lbfgs_update_history": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_lbfgs_direction_step": (c_i, [c_fp] * 6 + [c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_i64, c_i, c_fp]),

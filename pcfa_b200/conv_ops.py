@@ -32,7 +32,7 @@ def _dummy_like(shape, dtype, device, cl):
 
 class _ConvBiasAct(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0):
         lib = _lib.load()
         y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
         cl = _is_cl(y)
@@ -40,32 +40,32 @@ class _ConvBiasAct(Function):
             y = y.contiguous()
         C = y.shape[1]
         inner = 1 if cl else y.shape[2] * y.shape[3]
-        st = lib.pcfa_bias_act_forward(_lib.ptr(y), _lib.ptr(bias), y.numel(), C, inner, int(relu), 0 if y.dtype == torch.float32 else 1,
+        st = lib.pcfa_bias_act_forward(_lib.ptr(y), _lib.ptr(bias), y.numel(), C, inner, int(relu), float(slope), 0 if y.dtype == torch.float32 else 1,
                                        _lib.stream())
         if st == -1:                                 # PCFA_E_BADARG: shape the vector kernels do not take (e.g. 2 output channels)
             y.add_(bias.view(1, -1, 1, 1))
             if relu:
-                y.relu_()
+                y = F.leaky_relu_(y, slope) if slope else y.relu_()
         else:
             _lib.check(st, "pcfa_bias_act_forward")
         ctx.save_for_backward(weight, y if relu else None)
-        ctx.meta = (tuple(x.shape), x.dtype, x.device, _is_cl(x) or cl, stride, padding, dilation, groups, bool(relu))
+        ctx.meta = (tuple(x.shape), x.dtype, x.device, _is_cl(x) or cl, stride, padding, dilation, groups, bool(relu), float(slope))
         return y
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         weight, y = ctx.saved_tensors
-        shape, dtype, device, cl, stride, padding, dilation, groups, relu = ctx.meta
+        shape, dtype, device, cl, stride, padding, dilation, groups, relu, slope = ctx.meta
         if relu:
             g = g.contiguous(memory_format=_CL) if _is_cl(y) else g.contiguous()
             if g.dtype != y.dtype:
                 g = g.to(y.dtype)
             gx = torch.empty_like(y)
-            st = lib.pcfa_relu_mask_backward(_lib.ptr(y), _lib.ptr(g), _lib.ptr(gx), y.numel(), 0 if y.dtype == torch.float32 else 1,
+            st = lib.pcfa_relu_mask_backward(_lib.ptr(y), _lib.ptr(g), _lib.ptr(gx), y.numel(), slope, 0 if y.dtype == torch.float32 else 1,
                                              _lib.stream())
             if st == -1:
-                gx = g * (y > 0)
+                gx = torch.where(y > 0, g, g * slope)
             else:
                 _lib.check(st, "pcfa_relu_mask_backward")
             g = gx
@@ -73,11 +73,12 @@ class _ConvBiasAct(Function):
             g = g.to(weight.dtype)
         gin = torch.ops.aten.convolution_backward(g, _dummy_like(shape, dtype, device, cl), weight, None, stride, padding, dilation,
                                                   False, (0, 0), groups, (True, False, False))[0]
-        return gin, None, None, None, None, None, None, None
+        return gin, None, None, None, None, None, None, None, None
 
 
-def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16"):
-    """relu?(conv(x)) with `conv`'s geometry; `weight` / `bias` override the module's (e.g. batch-norm-folded copies)."""
+def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16", slope: float = 0.0):
+    """act?(conv(x)) with `conv`'s geometry (act = ReLU, or LeakyReLU(slope) for slope > 0); `weight` / `bias` override the
+    module's (e.g. batch-norm-folded copies)."""
     w = conv.weight if weight is None else weight
     b = conv.bias if bias is None else bias
     frozen = not (w.requires_grad or (b is not None and b.requires_grad))
@@ -88,6 +89,14 @@ def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bi
             if x.dtype != torch.float16:
                 x = x.to(torch.float16)
         if x.dtype == w.dtype and x.dtype in (torch.float32, torch.float16):
-            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu)
+            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu, slope)
     y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
-    return F.relu(y) if relu else y
+    return (F.leaky_relu(y, slope) if slope else F.relu(y)) if relu else y
+
+
+class ConvLeakyReLU(torch.nn.Sequential):
+    """nn.Sequential(Conv2d, LeakyReLU(slope)) with the same children and state-dict keys (PWCNet.py:23-28, FlowNet's
+    submodules.py conv()), evaluated through conv_act when the weights are frozen and the input is a CUDA tensor."""
+
+    def forward(self, x):
+        return conv_act(self[0], x, True, slope=float(self[1].negative_slope))

@@ -1,8 +1,8 @@
 // Bias + ReLU epilogue of the frozen convolutions (glue around the cuDNN convolutions).
 // torch's cuDNN convolution adds the bias in a separate broadcasting ATen kernel (non-vectorised: 8.5 us for a 3.6 MB
 // activation, 122 launches = 1.0 ms of one RAFT closure) and the ReLU in another (clamp, 99 launches, 0.47 ms).  Here the
-// convolution runs without bias and ONE in-place pass does y = max(x + b[c], 0); the backward is the ReLU mask
-// g * (y > 0) in one pass (what threshold_backward does).  fp32 and fp16 (GMA under autocast), channels-last or NCHW.
+// convolution runs without bias and ONE in-place pass does y = act(x + b[c]), act = ReLU or LeakyReLU(slope) (PWCNet and
+// FlowNet2 use slope 0.1); the backward is the mask y > 0 ? g : slope * g in one pass (what threshold_backward does).  fp32 and fp16 (GMA under autocast), channels-last or NCHW.
 // HBM/L2-bound: 8 bytes per element forward (in place), 12 backward.
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -14,7 +14,7 @@ constexpr int BA_THREADS = 256;
 // channel of flat element i:  channels-last: i % C   |   NCHW: (i / inner) % C     (inner = H*W, 1 for channels-last)
 template <bool RELU>
 __global__ void __launch_bounds__(BA_THREADS)
-bias_act_f32_kernel(float* __restrict__ x, const float* __restrict__ bias, int64_t n4, int C, int64_t inner) {
+bias_act_f32_kernel(float* __restrict__ x, const float* __restrict__ bias, int64_t n4, int C, int64_t inner, float slope) {
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
         float4 a = reinterpret_cast<float4*>(x)[v];
         const int64_t i = v * 4;
@@ -25,50 +25,50 @@ bias_act_f32_kernel(float* __restrict__ x, const float* __restrict__ bias, int64
             const float b = bias ? __ldg(bias + (int)((i / inner) % C)) : 0.f;     // inner % 4 == 0: one channel per vector
             a.x += b; a.y += b; a.z += b; a.w += b;
         }
-        if (RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        if (RELU) { a.x = fmaxf(a.x, slope * a.x); a.y = fmaxf(a.y, slope * a.y); a.z = fmaxf(a.z, slope * a.z); a.w = fmaxf(a.w, slope * a.w); }   // 0 <= slope < 1
         reinterpret_cast<float4*>(x)[v] = a;
     }
 }
 
 template <bool RELU>
 __global__ void __launch_bounds__(BA_THREADS)
-bias_act_f16_kernel(__half* __restrict__ x, const __half* __restrict__ bias, int64_t n8, int C, int64_t inner) {
+bias_act_f16_kernel(__half* __restrict__ x, const __half* __restrict__ bias, int64_t n8, int C, int64_t inner, float slope) {
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n8; v += (int64_t)gridDim.x * BA_THREADS) {
         uint4 raw = reinterpret_cast<uint4*>(x)[v];
         __half2* h = reinterpret_cast<__half2*>(&raw);
         const int64_t i = v * 8;
-        const __half2 zero = __float2half2_rn(0.f);
+        const __half2 sl = __float2half2_rn(slope);
         if (inner == 1) {
             const uint4 braw = __ldg(reinterpret_cast<const uint4*>(bias + (int)(i % C)));
             const __half2* b = reinterpret_cast<const __half2*>(&braw);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { h[k] = __hadd2(h[k], b[k]); if (RELU) h[k] = __hmax2(h[k], zero); }
+            for (int k = 0; k < 4; ++k) { h[k] = __hadd2(h[k], b[k]); if (RELU) h[k] = __hmax2(h[k], __hmul2(h[k], sl)); }
         } else {
             const __half2 b = __half2half2(__ldg(bias + (int)((i / inner) % C)));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { h[k] = __hadd2(h[k], b); if (RELU) h[k] = __hmax2(h[k], zero); }
+            for (int k = 0; k < 4; ++k) { h[k] = __hadd2(h[k], b); if (RELU) h[k] = __hmax2(h[k], __hmul2(h[k], sl)); }
         }
         reinterpret_cast<uint4*>(x)[v] = raw;
     }
 }
 
 __global__ void __launch_bounds__(BA_THREADS)
-relu_mask_f32_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, int64_t n4) {
+relu_mask_f32_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, int64_t n4, float slope) {
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(y) + v), g = __ldg(reinterpret_cast<const float4*>(gy) + v);
-        reinterpret_cast<float4*>(gx)[v] = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+        reinterpret_cast<float4*>(gx)[v] = make_float4(a.x > 0.f ? g.x : slope * g.x, a.y > 0.f ? g.y : slope * g.y, a.z > 0.f ? g.z : slope * g.z, a.w > 0.f ? g.w : slope * g.w);
     }
 }
 
 __global__ void __launch_bounds__(BA_THREADS)
-relu_mask_f16_kernel(const __half* __restrict__ y, const __half* __restrict__ gy, __half* __restrict__ gx, int64_t n8) {
+relu_mask_f16_kernel(const __half* __restrict__ y, const __half* __restrict__ gy, __half* __restrict__ gx, int64_t n8, float slope) {
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n8; v += (int64_t)gridDim.x * BA_THREADS) {
         const uint4 ar = __ldg(reinterpret_cast<const uint4*>(y) + v);
         uint4 gr = __ldg(reinterpret_cast<const uint4*>(gy) + v);
         const __half* a = reinterpret_cast<const __half*>(&ar);
         __half* g = reinterpret_cast<__half*>(&gr);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (!(__half2float(a[k]) > 0.f)) g[k] = __float2half_rn(0.f);
+        for (int k = 0; k < 8; ++k) if (!(__half2float(a[k]) > 0.f)) g[k] = __float2half_rn(slope * __half2float(g[k]));
         reinterpret_cast<uint4*>(gx)[v] = gr;
     }
 }
@@ -85,32 +85,33 @@ using namespace pcfa;
 
 // x: n elements, in place.  dtype 0 = fp32 (vector 4), 1 = fp16 (vector 8).  channels-last: inner = 1 and C % vector == 0;
 // NCHW: inner = H*W with inner % vector == 0.  n % vector == 0; x (and bias for channels-last) 16-byte aligned.
-extern "C" int pcfa_bias_act_forward(void* x, const void* bias, int64_t n, int C, int64_t inner, int relu, int dtype,
+extern "C" int pcfa_bias_act_forward(void* x, const void* bias, int64_t n, int C, int64_t inner, int relu, float slope, int dtype,
                                      pcfa_stream_t stream) {
-    if (!x || !bias || n <= 0 || C <= 0 || inner <= 0 || dtype < 0 || dtype > 1) return PCFA_E_BADARG;
+    if (!x || !bias || n <= 0 || C <= 0 || inner <= 0 || dtype < 0 || dtype > 1 || !(slope >= 0.f && slope < 1.f)) return PCFA_E_BADARG;
     const int vec = dtype == 0 ? 4 : 8;
     if (n % vec || (reinterpret_cast<uintptr_t>(x) & 15)) return PCFA_E_BADARG;
     if (inner == 1 ? (C % vec || (reinterpret_cast<uintptr_t>(bias) & 15)) : (inner % vec != 0)) return PCFA_E_BADARG;
     const int64_t nv = n / vec;
     cudaStream_t s = as_stream(stream);
     if (dtype == 0) {
-        if (relu) bias_act_f32_kernel<true><<<ba_grid(nv), BA_THREADS, 0, s>>>((float*)x, (const float*)bias, nv, C, inner);
-        else      bias_act_f32_kernel<false><<<ba_grid(nv), BA_THREADS, 0, s>>>((float*)x, (const float*)bias, nv, C, inner);
+        if (relu) bias_act_f32_kernel<true><<<ba_grid(nv), BA_THREADS, 0, s>>>((float*)x, (const float*)bias, nv, C, inner, slope);
+        else      bias_act_f32_kernel<false><<<ba_grid(nv), BA_THREADS, 0, s>>>((float*)x, (const float*)bias, nv, C, inner, slope);
     } else {
-        if (relu) bias_act_f16_kernel<true><<<ba_grid(nv), BA_THREADS, 0, s>>>((__half*)x, (const __half*)bias, nv, C, inner);
-        else      bias_act_f16_kernel<false><<<ba_grid(nv), BA_THREADS, 0, s>>>((__half*)x, (const __half*)bias, nv, C, inner);
+        if (relu) bias_act_f16_kernel<true><<<ba_grid(nv), BA_THREADS, 0, s>>>((__half*)x, (const __half*)bias, nv, C, inner, slope);
+        else      bias_act_f16_kernel<false><<<ba_grid(nv), BA_THREADS, 0, s>>>((__half*)x, (const __half*)bias, nv, C, inner, slope);
     }
     return after_launch();
 }
 
-// grad_x = grad_y * (y > 0); any dense layout (element-wise), n % vector == 0, 16-byte aligned pointers
-extern "C" int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int64_t n, int dtype, pcfa_stream_t stream) {
-    if (!y || !grad_y || !grad_x || n <= 0 || dtype < 0 || dtype > 1) return PCFA_E_BADARG;
+// grad_x = y > 0 ? grad_y : slope * grad_y; any dense layout (element-wise), n % vector == 0, 16-byte aligned pointers
+extern "C" int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int64_t n, float slope, int dtype,
+                                       pcfa_stream_t stream) {
+    if (!y || !grad_y || !grad_x || n <= 0 || dtype < 0 || dtype > 1 || !(slope >= 0.f && slope < 1.f)) return PCFA_E_BADARG;
     const int vec = dtype == 0 ? 4 : 8;
     if (n % vec || ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(grad_x)) & 15))
         return PCFA_E_BADARG;
     const int64_t nv = n / vec;
-    if (dtype == 0) relu_mask_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const float*)y, (const float*)grad_y, (float*)grad_x, nv);
-    else            relu_mask_f16_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const __half*)y, (const __half*)grad_y, (__half*)grad_x, nv);
+    if (dtype == 0) relu_mask_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const float*)y, (const float*)grad_y, (float*)grad_x, nv, slope);
+    else            relu_mask_f16_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const __half*)y, (const __half*)grad_y, (__half*)grad_x, nv, slope);
     return after_launch();
 }

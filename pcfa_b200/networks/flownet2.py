@@ -14,7 +14,8 @@ from torch.nn import init
 
 
 def conv(cin, cout, kernel_size=3, stride=1):
-    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=True),
+    from ..conv_ops import ConvLeakyReLU             # same children / state-dict keys as nn.Sequential(conv, LeakyReLU)
+    return ConvLeakyReLU(nn.Conv2d(cin, cout, kernel_size=kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=True),
                          nn.LeakyReLU(0.1, inplace=True))
 
 

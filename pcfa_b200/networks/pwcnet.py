@@ -14,7 +14,8 @@ import torch.nn as nn
 
 
 def conv(cin, cout, kernel_size=3, stride=1, padding=1, dilation=1):
-    return nn.Sequential(nn.Conv2d(int(cin), int(cout), kernel_size=kernel_size, stride=stride, padding=padding,
+    from ..conv_ops import ConvLeakyReLU             # same children / state-dict keys as nn.Sequential(conv, LeakyReLU)
+    return ConvLeakyReLU(nn.Conv2d(int(cin), int(cout), kernel_size=kernel_size, stride=stride, padding=padding,
                                    dilation=dilation, bias=True), nn.LeakyReLU(0.1))
 
 

@@ -506,12 +506,12 @@ def test_conv_act_matches_conv_bias_relu(cl, dtype, cin, cout, k, stride):
     if cl:
         conv = conv.to(memory_format=torch.channels_last)
         x = x.contiguous(memory_format=torch.channels_last)
-    for relu in (True, False):
+    for relu, slope in ((True, 0.0), (False, 0.0), (True, 0.1)):          # ReLU, none, LeakyReLU(0.1) (PWCNet / FlowNet2)
         a = x.clone().requires_grad_(True)
         b = x.clone().requires_grad_(True)
-        y = conv_act(conv, a, relu)
+        y = conv_act(conv, a, relu, slope=slope)
         ref = conv(b)
-        ref = torch.relu(ref) if relu else ref
+        ref = (torch.nn.functional.leaky_relu(ref, slope) if slope else torch.relu(ref)) if relu else ref
         tol = dict(rtol=1e-3, atol_rms=1e-3) if dtype == torch.float32 else dict(rtol=1e-2, atol_rms=1e-2)
         assert_close(npy(y), npy(ref), what="conv_act fwd", **tol)
         go = torch.randn(ref.shape, generator=g).cuda().to(dtype)
