@@ -392,6 +392,19 @@ def bench_universal(args, net, device, world, rank, barrier):
         ar_us = round(us[len(us) // 2], 1)
     loss = float(flat[-1].item())
     gn = float(flat[:n].norm().item())
+    corr_rows = None
+    if rank == 0:
+        # the correlation entry points at batch %d (where they are not launch-latency-bound), same instrumented eager pass as
+        # the headline kernel table
+        try:
+            from pcfa_b200 import profiling
+            peak, _ = peaks()
+            tab = profiling.kernel_table(lambda: fo.evaluate(delta, None, g1), n_steps=2, B=P, C=256, H=a.shape[2] // 8, W=a.shape[3] // 8,
+                                         iters=12, peak_gbs=peak, img_numel=a.numel(), flow_numel=2 * P * a.shape[2] * a.shape[3])
+            corr_rows = [{k: r[k] for k in ("name", "launches_per_step", "avg_us", "algorithmic_bytes", "achieved_gbs", "frac_of_hbm_peak") if k in r}
+                         for r in tab if r["name"].startswith("pcfa_corr_") and r.get("algorithmic_bytes")]
+        except Exception as e:
+            corr_rows = {"error": repr(e)[:200]}
     del ev, fo
     torch.cuda.empty_cache()
     return {"workload": "RAFT universal-joint perturbation, clipping, zero target, aee, 12 GRU iters, %dx%d, %d pairs per GPU "
@@ -401,7 +414,7 @@ def bench_universal(args, net, device, world, rank, barrier):
             "allreduce": "none (1 rank)" if world == 1 else "NCCL all_reduce(sum) of [grad_delta | loss] = %d bytes per closure on the compute stream, then 1/world" % (4 * (n + 1)),
             "allreduce_bytes": 4 * (n + 1), "allreduce_us_median": ar_us, "scaling": "weak",
             "efficiency_definition": "ms_per_closure(N=1) / ms_per_closure(N), both at %d pairs per GPU" % P,
-            "loss": loss, "grad_norm": gn, "cuda_graph": not args.no_graph}
+            "loss": loss, "grad_norm": gn, "cuda_graph": not args.no_graph, "corr_kernels_at_batch": corr_rows}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
