@@ -398,6 +398,14 @@ int pcfa_lbfgs_update_history(const float* grad, float* grad_prev, const float* 
 int pcfa_lbfgs_direction_step(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag, float* d,
                               const int* ring, float* param, float t, float tol_change, float* scalars_out, void* workspace,
                               int64_t n, int history_capacity, pcfa_stream_t stream);
+/* The same direction in the compact (Byrd-Nocedal-Schnabel) representation: three launches without a grid barrier instead
+ * of one cooperative launch with 2*num_old of them (csrc/lbfgs_compact.cu).  pair_scalars = the {<y,s>, <y,y>} that
+ * pcfa_lbfgs_update_history wrote; `state` (pcfa_lbfgs_compact_workspace_bytes(history_capacity), zero-initialised, 8-byte
+ * aligned) carries S^T Y, Y^T Y and the previous S^T grad, Y^T grad between calls. */
+int64_t pcfa_lbfgs_compact_workspace_bytes(int history_capacity);
+int pcfa_lbfgs_direction_compact(const float* S, const float* Y, const float* grad, const float* h_diag, float* d, const int* ring,
+                                 const float* pair_scalars, float* param, float t, float tol_change, float* scalars_out,
+                                 void* state, int64_t n, int history_capacity, pcfa_stream_t stream);
 int pcfa_lbfgs_store_pair(const float* grad, float* grad_prev, const float* d, float t, float* s_slot, float* y_slot,
                           float* scalars_out, void* workspace, int64_t n, pcfa_stream_t stream);
 int pcfa_lbfgs_direction(const float* S, const float* Y, const float* ro, const float* grad, const float* h_diag, float* d,

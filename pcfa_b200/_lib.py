@@ -76,6 +76,8 @@ SIGNATURES = {
     "pcfa_relu_mask_backward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_f, c_i, c_fp]),
     "pcfa_lbfgs_workspace_bytes": (c_i64, []),
     "pcfa_lbfgs_update_history": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
+    "pcfa_lbfgs_compact_workspace_bytes": (c_i64, [c_i]),
+    "pcfa_lbfgs_direction_compact": (c_i, [c_fp] * 5 + [c_fp, c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_lbfgs_direction_step": (c_i, [c_fp] * 6 + [c_fp, c_fp, c_f, c_f, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_lbfgs_store_pair": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_lbfgs_direction": (c_i, [c_fp] * 8 + [c_i64, c_i, c_i, c_i, c_fp]),

@@ -164,6 +164,7 @@ lbfgs_pair_commit_kernel(const float* __restrict__ g, float* __restrict__ g_prev
             ro[slot] = 1.0f / ys;
             *hdiag = ys / yy;
         } else { ring_out[0] = start; ring_out[1] = num_old; }
+        ring_out[2] = accept ? 1 : 0;                          // read by the compact direction (lbfgs_compact.cu)
     }
     float* s_out = S + (int64_t)slot * n;
     float* y_out = Y + (int64_t)slot * n;
@@ -251,7 +252,7 @@ static int lb_coop_grid(int64_t n, int* grid_out) {
     return PCFA_OK;
 }
 
-// History update decided on the device: scalars_out = {<y,s>, <y,y>}; ring_in / ring_out: int[2] = {start, num_old}.
+// History update decided on the device: scalars_out = {<y,s>, <y,y>}; ring_in / ring_out: int[4] = {start, num_old, accepted, -}.
 extern "C" int pcfa_lbfgs_update_history(const float* grad, float* grad_prev, const float* d, float t, float* S, float* Y, float* ro,
                                          float* h_diag, const int* ring_in, int* ring_out, float* scalars_out, void* workspace,
                                          int64_t n, int history_capacity, pcfa_stream_t stream) {

@@ -5,8 +5,10 @@ attack_PCFA.py:97,114 with max_iter=10 and defaults lr=1, max_eval=12, tolerance
 history_size=100, no line search) decision for decision, but keeps the parameters, the gradient and the (s, y)
 history in flat device buffers and runs the vector algebra in four launches per iteration instead of ~4*history:
     pcfa_lbfgs_update_history  (<y,s>, <y,y>; curvature test, ring-buffer update, ro, H_diag decided on the device)
-    pcfa_lbfgs_direction_step  (two-loop recursion, <g,d>, max|d|, then param += t*d unless <g,d> > -tolerance_change:
-                                one cooperative launch)
+    pcfa_lbfgs_direction_compact (default; the same H_k in the compact Byrd-Nocedal-Schnabel form: one pass for S^T g, Y^T g,
+                                a single-CTA double-precision solve, one pass for d and param += t*d unless
+                                <g,d> > -tolerance_change — no chain of 2*history grid barriers), or
+    pcfa_lbfgs_direction_step  (direction="two_loop": torch's two-loop recursion literally, one cooperative launch)
 Host round trips: ONE small D2H read per inner iteration, after its closure (the stopping tests torch syncs on one by
 one, packed), none on the last iteration of a step."""
 from __future__ import annotations
@@ -18,7 +20,7 @@ from . import _lib
 
 class DeviceLBFGS:
     def __init__(self, flat_param: torch.Tensor, flat_grad: torch.Tensor, lr=1.0, max_iter=10, max_eval=None,
-                 tolerance_grad=1e-7, tolerance_change=1e-9, history_size=100):
+                 tolerance_grad=1e-7, tolerance_change=1e-9, history_size=100, direction="compact"):
         if not (flat_param.is_cuda and flat_param.dtype == torch.float32 and flat_param.dim() == 1 and flat_param.is_contiguous()):
             raise RuntimeError("DeviceLBFGS: flat_param must be a contiguous 1-D CUDA float32 tensor (pcfa_b200 has no CPU path)")
         if flat_grad.shape != flat_param.shape or not flat_grad.is_cuda or flat_grad.dtype != torch.float32:
@@ -37,10 +39,15 @@ class DeviceLBFGS:
         self.d = torch.empty(n, device=dev)
         self.g_prev = torch.empty(n, device=dev)
         self.sc = torch.zeros(4, device=dev)                     # {<y,s>, <y,y>, <g,d>, max|d|}
-        self.ring = torch.zeros(2, 2, dtype=torch.int32, device=dev)   # double-buffered {start, num_old}
+        self.ring = torch.zeros(2, 4, dtype=torch.int32, device=dev)   # double-buffered {start, num_old, accepted, -}
         self.cur = 0
+        if direction not in ("compact", "two_loop"):
+            raise ValueError("direction must be 'compact' or 'two_loop'")
+        self.direction = direction
         lib = _lib.load()
         self.ws = torch.empty(lib.pcfa_lbfgs_workspace_bytes(), device=dev, dtype=torch.uint8)
+        # compact direction: S^T Y, Y^T Y (double) and the previous S^T g, Y^T g live here between iterations
+        self.cstate = torch.zeros(lib.pcfa_lbfgs_compact_workspace_bytes(self.m) // 8 + 1, device=dev, dtype=torch.float64)
         self.state = dict(func_evals=0, n_iter=0, t=None, prev_loss=None)
 
     def step(self, closure):
@@ -67,8 +74,9 @@ class DeviceLBFGS:
             first = st["n_iter"] == 1
             if first:
                 torch.neg(self.g, out=self.d)
-                self.ring[0].zero_()
+                self.ring.zero_()
                 self.cur = 0
+                self.cstate.zero_()
                 self.hdiag.fill_(1.0)
                 self.g_prev.copy_(self.g)
                 gtd = -float(self.g.dot(self.g))
@@ -87,9 +95,14 @@ class DeviceLBFGS:
                            "pcfa_lbfgs_update_history")
                 self.cur ^= 1
                 t = self.lr
-                _lib.check(lib.pcfa_lbfgs_direction_step(P(self.S), P(self.Y), P(self.ro), P(self.g), P(self.hdiag), P(self.d), P(ring_out),
-                                                         P(self.p), float(t), float(self.tolerance_change), P(self.sc[2:]), P(self.ws),
-                                                         self.n, self.m, s), "pcfa_lbfgs_direction_step")
+                if self.direction == "compact":
+                    _lib.check(lib.pcfa_lbfgs_direction_compact(P(self.S), P(self.Y), P(self.g), P(self.hdiag), P(self.d), P(ring_out), P(self.sc),
+                                                                P(self.p), float(t), float(self.tolerance_change), P(self.sc[2:]),
+                                                                P(self.cstate), self.n, self.m, s), "pcfa_lbfgs_direction_compact")
+                else:
+                    _lib.check(lib.pcfa_lbfgs_direction_step(P(self.S), P(self.Y), P(self.ro), P(self.g), P(self.hdiag), P(self.d), P(ring_out),
+                                                             P(self.p), float(t), float(self.tolerance_change), P(self.sc[2:]), P(self.ws),
+                                                             self.n, self.m, s), "pcfa_lbfgs_direction_step")
             prev_loss = loss
             if n_iter == self.max_iter:
                 break                                         # torch evaluates no closure on the last iteration: no read-back either

@@ -17,8 +17,9 @@ def _problem(n, seed):
     return f, x0
 
 
-@pytest.mark.parametrize("n,history,steps", [(5000, 100, 3), (1003, 5, 4), (200000, 100, 2)])
-def test_device_lbfgs_matches_torch_lbfgs(n, history, steps):
+@pytest.mark.parametrize("direction", ["compact", "two_loop"])
+@pytest.mark.parametrize("n,history,steps", [(5000, 100, 3), (1003, 5, 4), (200000, 100, 2), (4096, 7, 6)])
+def test_device_lbfgs_matches_torch_lbfgs(n, history, steps, direction):
     from pcfa_b200.lbfgs import DeviceLBFGS
     f, x0 = _problem(n, n + history)
     # torch
@@ -34,7 +35,7 @@ def test_device_lbfgs_matches_torch_lbfgs(n, history, steps):
         return l
     # device
     flat_p, flat_g = x0.clone(), torch.zeros_like(x0)
-    dev = DeviceLBFGS(flat_p, flat_g, max_iter=10, history_size=history)
+    dev = DeviceLBFGS(flat_p, flat_g, max_iter=10, history_size=history, direction=direction)
     evals_d = [0]
 
     def closure_d():
