@@ -32,7 +32,7 @@ def _dummy_like(shape, dtype, device, cl):
 
 class _ConvBiasAct(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0, tail=None):
         lib = _lib.load()
         y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
         cl = _is_cl(y)
@@ -48,6 +48,8 @@ class _ConvBiasAct(Function):
                 y = F.leaky_relu_(y, slope) if slope else y.relu_()
         else:
             _lib.check(st, "pcfa_bias_act_forward")
+        if tail is not None:                         # overwrite the last channels (zero filters there): a cat without the copy
+            y[:, y.shape[1] - tail.shape[1]:] = tail
         ctx.save_for_backward(weight, y if relu else None)
         ctx.meta = (tuple(x.shape), x.dtype, x.device, _is_cl(x) or cl, stride, padding, dilation, groups, bool(relu), float(slope))
         return y
@@ -73,12 +75,33 @@ class _ConvBiasAct(Function):
             g = g.to(weight.dtype)
         gin = torch.ops.aten.convolution_backward(g, _dummy_like(shape, dtype, device, cl), weight, None, stride, padding, dilation,
                                                   False, (0, 0), groups, (True, False, False))[0]
-        return gin, None, None, None, None, None, None, None, None
+        return gin, None, None, None, None, None, None, None, None, None
 
 
-def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16", slope: float = 0.0):
+def padded_out_channels(conv: torch.nn.Conv2d, multiple: int = 8):
+    """(weight, bias) of a frozen convolution with zero filters appended so that the output channel count is a multiple of
+    `multiple`: cuDNN's sm_100 NHWC kernels otherwise wrap the convolution (and its data gradient) in channel-padding
+    launches (nhwcAddPaddingKernel: 76 launches, 0.28 ms per RAFT closure for the 126- and 2-channel outputs).  Cached."""
+    key = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version, multiple)
+    cache = getattr(conv, "_pcfa_padded", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            co = conv.weight.shape[0]
+            extra = (-co) % multiple
+            w = torch.cat([conv.weight, conv.weight.new_zeros((extra,) + tuple(conv.weight.shape[1:]))], 0)
+            if _is_cl(conv.weight):
+                w = w.contiguous(memory_format=_CL)
+            b = torch.cat([conv.bias, conv.bias.new_zeros(extra)], 0).contiguous()
+        cache = (key, w, b)
+        conv._pcfa_padded = cache
+    return cache[1], cache[2]
+
+
+def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16", slope: float = 0.0,
+             tail=None):
     """act?(conv(x)) with `conv`'s geometry (act = ReLU, or LeakyReLU(slope) for slope > 0); `weight` / `bias` override the
-    module's (e.g. batch-norm-folded copies)."""
+    module's (e.g. batch-norm-folded copies).  `tail` ([B, k, H, W], no gradient): written over the LAST k output channels
+    (which the caller has given zero filters, see padded_out_channels) — torch.cat([conv_out, tail], 1) without the copy."""
     w = conv.weight if weight is None else weight
     b = conv.bias if bias is None else bias
     frozen = not (w.requires_grad or (b is not None and b.requires_grad))
@@ -89,9 +112,12 @@ def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bi
             if x.dtype != torch.float16:
                 x = x.to(torch.float16)
         if x.dtype == w.dtype and x.dtype in (torch.float32, torch.float16):
-            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu, slope)
+            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu, slope, tail)
     y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
-    return (F.leaky_relu(y, slope) if slope else F.relu(y)) if relu else y
+    y = (F.leaky_relu(y, slope) if slope else F.relu(y)) if relu else y
+    if tail is not None:
+        y = torch.cat([y[:, :y.shape[1] - tail.shape[1]], tail], 1)
+    return y
 
 
 class ConvLeakyReLU(torch.nn.Sequential):

@@ -211,8 +211,14 @@ class FlowHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        from ..conv_ops import conv_act
-        return conv_act(self.conv2, conv_act(self.conv1, x, True), False)
+        from ..conv_ops import conv_act, padded_out_channels
+        y = conv_act(self.conv1, x, True)
+        frozen = not any(p.requires_grad for p in self.conv2.parameters())
+        if y.is_cuda and frozen and y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous() \
+                and os.environ.get("PCFA_PAD_CHANNELS", "1") != "0":
+            w, b = padded_out_channels(self.conv2, 8)            # 2 -> 8 output channels (zero filters): see padded_out_channels
+            return conv_act(self.conv2, y, False, w, b, "_pcfa_pad16")[:, :self.conv2.out_channels]
+        return conv_act(self.conv2, y, False)
 
 
 def _zr_weights(cz: nn.Conv2d, cr: nn.Conv2d):
@@ -324,7 +330,17 @@ class BasicMotionEncoder(nn.Module):
         from ..conv_ops import conv_act
         cor = conv_act(self.convc2, conv_act(self.convc1, corr, True), True)
         flo = conv_act(self.convf2, conv_act(self.convf1, flow, True), True)
-        out = conv_act(self.conv, cat_channels([cor, flo], cl), True)
+        x = cat_channels([cor, flo], cl)
+        frozen = not any(p.requires_grad for p in self.conv.parameters())
+        if cl and frozen and x.is_cuda and not flow.requires_grad and (self.conv.out_channels + flow.shape[1]) % 8 == 0 \
+                and os.environ.get("PCFA_PAD_CHANNELS", "1") != "0":
+            # 126 -> 128 output channels with two zero filters, the flow written over them: no cuDNN channel padding
+            # around the convolution and its data gradient, and torch.cat([out, flow]) costs a 56 KB strided write
+            from ..conv_ops import padded_out_channels
+            w, b = padded_out_channels(self.conv, 8)
+            if w.shape[0] == self.conv.out_channels + flow.shape[1]:
+                return conv_act(self.conv, x, True, w, b, "_pcfa_pad16", tail=flow)
+        out = conv_act(self.conv, x, True)
         return cat_channels([out, flow], cl)
 
 
