@@ -12,3 +12,7 @@ python scripts/bench_vs_reference_gpu.py > gpurun_out/bvr_r2.log 2>&1
 python scripts/attack_breakdown.py > gpurun_out/attack_breakdown_r2.txt 2>&1
 for b in 1 8; do for i in 1 2; do B=$b PCFA_LOOKUP_IMPL=$i python scripts/bench_lookup.py; done; done > gpurun_out/bench_lookup_r2.txt 2>&1
 tail -3 gpurun_out/bench_configs_r2.log
+# one --set full capture of the correlation kernels (a single closure inside a profiler range)
+ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'corr_lookup|corr_pyramid|prep_targets|bw_prep|bw_unpool' -o gpurun_out/corr_r2 -f python scripts/run_closure.py > gpurun_out/ncu_corr_r2.log 2>&1
+python scripts/g_sparsity.py 1.0 > gpurun_out/g_sparsity_r2.txt 2>&1; python scripts/g_sparsity.py 0.5 >> gpurun_out/g_sparsity_r2.txt 2>&1
