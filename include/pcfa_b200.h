@@ -293,6 +293,12 @@ int pcfa_instnorm_forward(const float* x, float* y, float* stats, void* workspac
                           int relu, int channels_last, pcfa_stream_t stream);
 int pcfa_instnorm_backward(const float* x, const float* grad_y, const float* stats, float* grad_x, void* workspace,
                            int B, int C, int H, int W, int relu, int channels_last, pcfa_stream_t stream);
+/* Channels-last with x stored in fp16 (GMA's fp16-autocast encoder): y and grad_y fp32, grad_x fp16, fp32 arithmetic — what
+ * autocast makes of F.instance_norm(conv_out), without the conversion copies around it. */
+int pcfa_instnorm_forward_h(const void* x_half, float* y, float* stats, void* workspace, int B, int C, int H, int W, float eps,
+                            int relu, pcfa_stream_t stream);
+int pcfa_instnorm_backward_h(const void* x_half, const float* grad_y, const float* stats, void* grad_x_half, void* workspace, int B,
+                             int C, int H, int W, int relu, pcfa_stream_t stream);
 
 /* Element-wise halves of the convolutional GRU (models/raft/update.py:16-60): z = sigmoid, r = sigmoid, rh = r*h from the
  * concatenated pre-activations zr = [B][2C][H*W] (z first; n = C*H*W elements per sample), and the state update

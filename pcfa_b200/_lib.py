@@ -61,6 +61,8 @@ SIGNATURES = {
     "pcfa_objective_workspace_bytes": (c_i64, []),
     "pcfa_instnorm_workspace_bytes": (c_i64, [c_i, c_i, c_i, c_i]),
     "pcfa_instnorm_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_fp]),
+    "pcfa_instnorm_forward_h": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_f, c_i, c_fp]),
+    "pcfa_instnorm_backward_h": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_gru_gates_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_i, c_fp]),
     "pcfa_gru_gates_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i64, c_i, c_fp]),
     "pcfa_gru_blend_forward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),

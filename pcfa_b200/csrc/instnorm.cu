@@ -10,6 +10,7 @@
 // A plane (b, c) is cut into `splits` contiguous chunks, one CTA each, so small batches still fill the GPU; the chunk
 // partials are combined in double by every CTA of the second kernel (deterministic, no atomics).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace pcfa {
 
@@ -144,9 +145,31 @@ constexpr int IN_MAX_C = 1024;
 constexpr int INL_THREADS = 1024;
 constexpr int INL_U = 4;
 
-template <int MODE>
+// 4 consecutive channels as float4 from fp32 or fp16 storage (the fp16 variant serves GMA's autocast encoder: the
+// convolution output is normalised straight from half precision with fp32 arithmetic, which is what autocast makes of
+// F.instance_norm(conv_out.float()) without the 58 MB conversion copies around it)
+template <typename T> struct In4;
+template <> struct In4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct In4<__half> {
+    static __device__ __forceinline__ float4 ld(const __half* p) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ void st(__half* p, float4 v) {
+        uint2 r;
+        *reinterpret_cast<__half2*>(&r.x) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(&r.y) = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(p) = r;
+    }
+};
+
+template <int MODE, typename TX>
 __global__ void __launch_bounds__(INL_THREADS)
-instnorm_partial_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ stats,
+instnorm_partial_nhwc_kernel(const TX* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ stats,
                              float2* __restrict__ part, int64_t hw, int C, int splits, int relu) {
     extern __shared__ float sm[];                         // [2][rpi][C]
     const int b = blockIdx.y, tpr = C >> 2, rpi = INL_THREADS / tpr;
@@ -160,7 +183,7 @@ instnorm_partial_nhwc_kernel(const float* __restrict__ x, const float* __restric
 #pragma unroll
             for (int k = 0; k < 4; ++k) { const float2 st = stats[(int64_t)b * C + 4 * cg + k]; mean[k] = st.x; rstd[k] = st.y; }
         }
-        const float* xp = x + ((int64_t)b * hw) * C + 4 * cg;
+        const TX* xp = x + ((int64_t)b * hw) * C + 4 * cg;
         const float* gp = MODE == 1 ? dy + ((int64_t)b * hw) * C + 4 * cg : nullptr;
         for (int64_t row0 = lo + r; row0 < hi; row0 += (int64_t)INL_U * rpi) {
             float4 xv4[INL_U], gv4[INL_U];
@@ -169,7 +192,7 @@ instnorm_partial_nhwc_kernel(const float* __restrict__ x, const float* __restric
                 const int64_t row = row0 + (int64_t)u * rpi;
                 xv4[u] = make_float4(0.f, 0.f, 0.f, 0.f); gv4[u] = xv4[u];
                 if (row < hi) {
-                    xv4[u] = __ldg(reinterpret_cast<const float4*>(xp + row * C));
+                    xv4[u] = In4<TX>::ld(xp + row * C);
                     if (MODE == 1) gv4[u] = __ldg(reinterpret_cast<const float4*>(gp + row * C));
                 }
             }
@@ -200,10 +223,11 @@ instnorm_partial_nhwc_kernel(const float* __restrict__ x, const float* __restric
     }
 }
 
-template <int MODE>
+// TO: forward (MODE 0) writes fp32 (autocast's instance norm returns fp32); backward (MODE 1) writes the gradient in x's type
+template <int MODE, typename TX, typename TO>
 __global__ void __launch_bounds__(INL_THREADS)
-instnorm_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ part,
-                           float2* __restrict__ stats, float* __restrict__ out, int64_t hw, int C, int splits, float eps,
+instnorm_apply_nhwc_kernel(const TX* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ part,
+                           float2* __restrict__ stats, TO* __restrict__ out, int64_t hw, int C, int splits, float eps,
                            int relu) {
     extern __shared__ float sm[];                         // [4][C] mean, rstd, m1, m2 ; then [slots][C] double2 scratch
     float* s_mean = sm; float* s_rstd = sm + C; float* s_m1 = sm + 2 * C; float* s_m2 = sm + 3 * C;
@@ -247,9 +271,9 @@ instnorm_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict_
         mean[k] = s_mean[4 * cg + k]; rstd[k] = s_rstd[4 * cg + k];
         m1[k] = MODE == 1 ? s_m1[4 * cg + k] : 0.f; m2[k] = MODE == 1 ? s_m2[4 * cg + k] : 0.f;
     }
-    const float* xp = x + ((int64_t)b * hw) * C + 4 * cg;
+    const TX* xp = x + ((int64_t)b * hw) * C + 4 * cg;
     const float* gp = MODE == 1 ? dy + ((int64_t)b * hw) * C + 4 * cg : nullptr;
-    float* op = out + ((int64_t)b * hw) * C + 4 * cg;
+    TO* op = out + ((int64_t)b * hw) * C + 4 * cg;
     for (int64_t row0 = lo + r; row0 < hi; row0 += (int64_t)INL_U * rpi) {
         float4 xv4[INL_U], gv4[INL_U];
 #pragma unroll
@@ -257,7 +281,7 @@ instnorm_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict_
             const int64_t row = row0 + (int64_t)u * rpi;
             xv4[u] = make_float4(0.f, 0.f, 0.f, 0.f); gv4[u] = xv4[u];
             if (row < hi) {
-                xv4[u] = __ldg(reinterpret_cast<const float4*>(xp + row * C));
+                xv4[u] = In4<TX>::ld(xp + row * C);
                 if (MODE == 1) gv4[u] = __ldg(reinterpret_cast<const float4*>(gp + row * C));
             }
         }
@@ -277,7 +301,7 @@ instnorm_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict_
                     o[k] = rstd[k] * (g - m1[k] - xh * m2[k]);
                 }
             }
-            *reinterpret_cast<float4*>(op + row * C) = make_float4(o[0], o[1], o[2], o[3]);
+            In4<TO>::st(op + row * C, make_float4(o[0], o[1], o[2], o[3]));
         }
     }
 }
@@ -325,9 +349,9 @@ extern "C" int pcfa_instnorm_forward(const float* x, float* y, float* stats, voi
         cudaStream_t s = as_stream(stream);
         float2* part = reinterpret_cast<float2*>(workspace);
         dim3 grid(splits, B);
-        instnorm_partial_nhwc_kernel<0><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, nullptr, nullptr, part, hw, C, splits, relu);
+        instnorm_partial_nhwc_kernel<0, float><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, nullptr, nullptr, part, hw, C, splits, relu);
         PCFA_TRY(after_launch());
-        instnorm_apply_nhwc_kernel<0><<<grid, INL_THREADS, sm_apply, s>>>(x, nullptr, part, reinterpret_cast<float2*>(stats),
+        instnorm_apply_nhwc_kernel<0, float, float><<<grid, INL_THREADS, sm_apply, s>>>(x, nullptr, part, reinterpret_cast<float2*>(stats),
                                                                           y, hw, C, splits, eps, relu);
         return after_launch();
     }
@@ -359,9 +383,9 @@ extern "C" int pcfa_instnorm_backward(const float* x, const float* grad_y, const
         float2* part = reinterpret_cast<float2*>(workspace);
         float2* st = reinterpret_cast<float2*>(const_cast<float*>(stats));
         dim3 grid(splits, B);
-        instnorm_partial_nhwc_kernel<1><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, grad_y, st, part, hw, C, splits, relu);
+        instnorm_partial_nhwc_kernel<1, float><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, grad_y, st, part, hw, C, splits, relu);
         PCFA_TRY(after_launch());
-        instnorm_apply_nhwc_kernel<1><<<grid, INL_THREADS, sm_apply, s>>>(x, grad_y, part, st, grad_x, hw, C, splits, 0.f, relu);
+        instnorm_apply_nhwc_kernel<1, float, float><<<grid, INL_THREADS, sm_apply, s>>>(x, grad_y, part, st, grad_x, hw, C, splits, 0.f, relu);
         return after_launch();
     }
     if (planes > 65535) return PCFA_E_TOOLARGE;
@@ -376,5 +400,48 @@ extern "C" int pcfa_instnorm_backward(const float* x, const float* grad_y, const
     PCFA_TRY(after_launch());
     instnorm_apply_kernel<1><<<grid, IN_THREADS, 0, s>>>(x, grad_y, part, const_cast<float2*>(st), grad_x, hw, splits, 0.f,
                                                          relu, vec);
+    return after_launch();
+}
+
+// Channels-last, x in fp16 (GMA's autocast encoder): y fp32; backward: grad_y fp32, grad_x fp16.  Same kernels, fp32 arithmetic.
+extern "C" int pcfa_instnorm_forward_h(const void* x_half, float* y, float* stats, void* workspace, int B, int C, int H, int W,
+                                       float eps, int relu, pcfa_stream_t stream) {
+    if (!x_half || !y || !stats || !workspace || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PCFA_E_BADARG;
+    if (!nhwc_ok(C, y, y, y) || (reinterpret_cast<uintptr_t>(x_half) & 7) || B > 65535) return PCFA_E_BADARG;
+    const int64_t hw = (int64_t)H * W;
+    const int splits = in_splits_nhwc(B, hw);
+    const int rpi = INL_THREADS / (C / 4);
+    const int slots = INL_THREADS / C > 0 ? INL_THREADS / C : 1;
+    const size_t sm_apply = 4 * C * sizeof(float) + (size_t)slots * C * 2 * sizeof(double);
+    cudaStream_t s = as_stream(stream);
+    float2* part = reinterpret_cast<float2*>(workspace);
+    const __half* x = reinterpret_cast<const __half*>(x_half);
+    dim3 grid(splits, B);
+    instnorm_partial_nhwc_kernel<0, __half><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, nullptr, nullptr, part, hw, C, splits, relu);
+    PCFA_TRY(after_launch());
+    instnorm_apply_nhwc_kernel<0, __half, float><<<grid, INL_THREADS, sm_apply, s>>>(x, nullptr, part, reinterpret_cast<float2*>(stats), y, hw, C,
+                                                                                     splits, eps, relu);
+    return after_launch();
+}
+
+extern "C" int pcfa_instnorm_backward_h(const void* x_half, const float* grad_y, const float* stats, void* grad_x_half, void* workspace,
+                                        int B, int C, int H, int W, int relu, pcfa_stream_t stream) {
+    if (!x_half || !grad_y || !stats || !grad_x_half || !workspace || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PCFA_E_BADARG;
+    if (!nhwc_ok(C, grad_y, grad_y, grad_y) || ((reinterpret_cast<uintptr_t>(x_half) | reinterpret_cast<uintptr_t>(grad_x_half)) & 7) || B > 65535)
+        return PCFA_E_BADARG;
+    const int64_t hw = (int64_t)H * W;
+    const int splits = in_splits_nhwc(B, hw);
+    const int rpi = INL_THREADS / (C / 4);
+    const int slots = INL_THREADS / C > 0 ? INL_THREADS / C : 1;
+    const size_t sm_apply = 4 * C * sizeof(float) + (size_t)slots * C * 2 * sizeof(double);
+    cudaStream_t s = as_stream(stream);
+    float2* part = reinterpret_cast<float2*>(workspace);
+    float2* st = reinterpret_cast<float2*>(const_cast<float*>(stats));
+    const __half* x = reinterpret_cast<const __half*>(x_half);
+    dim3 grid(splits, B);
+    instnorm_partial_nhwc_kernel<1, __half><<<grid, INL_THREADS, 2 * rpi * C * sizeof(float), s>>>(x, grad_y, st, part, hw, C, splits, relu);
+    PCFA_TRY(after_launch());
+    instnorm_apply_nhwc_kernel<1, __half, __half><<<grid, INL_THREADS, sm_apply, s>>>(x, grad_y, part, st, reinterpret_cast<__half*>(grad_x_half),
+                                                                                      hw, C, splits, 0.f, relu);
     return after_launch();
 }

@@ -15,6 +15,35 @@ def _is_cl(x: torch.Tensor) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
+class _InstNormHalfFn(Function):
+    """channels-last fp16 input (a convolution output under autocast) -> fp32 output; the gradient goes back in fp16."""
+
+    @staticmethod
+    def forward(ctx, x, eps, relu):
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        stats = torch.empty(B * C, 2, device=x.device, dtype=torch.float32)
+        ws = torch.empty(lib.pcfa_instnorm_workspace_bytes(B, C, H, W), device=x.device, dtype=torch.uint8)
+        _lib.check(lib.pcfa_instnorm_forward_h(_lib.ptr(x), _lib.ptr(y), _lib.ptr(stats), _lib.ptr(ws), B, C, H, W, float(eps), int(relu),
+                                               _lib.stream()), "pcfa_instnorm_forward_h")
+        ctx.save_for_backward(x, stats)
+        ctx.relu = int(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, stats = ctx.saved_tensors
+        gy = gy.float().contiguous(memory_format=torch.channels_last)
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        gx = torch.empty_like(x)
+        ws = torch.empty(lib.pcfa_instnorm_workspace_bytes(B, C, H, W), device=x.device, dtype=torch.uint8)
+        _lib.check(lib.pcfa_instnorm_backward_h(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(stats), _lib.ptr(gx), _lib.ptr(ws), B, C, H, W, ctx.relu,
+                                                _lib.stream()), "pcfa_instnorm_backward_h")
+        return gx, None, None
+
+
 class _InstNormFn(Function):
     @staticmethod
     def forward(ctx, x, eps, relu):
@@ -51,6 +80,8 @@ def instance_norm(x: torch.Tensor, eps: float = 1e-5, relu: bool = False) -> tor
     """relu?(F.instance_norm(x, eps=eps)) for a CUDA 4-D tensor (no affine, no running statistics).  Half-precision
     inputs (convolution outputs under autocast, GMA's default) are normalised in fp32 and returned in fp32, which is
     what autocast makes of F.instance_norm as well."""
+    if x.dtype == torch.float16 and x.is_cuda and x.dim() == 4 and _is_cl(x):
+        return _InstNormHalfFn.apply(x, eps, relu)            # no conversion copies (csrc/instnorm.cu, *_h entry points)
     if x.dtype != torch.float32:
         x = x.float()
     return _InstNormFn.apply(x, eps, relu)

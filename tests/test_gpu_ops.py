@@ -518,3 +518,26 @@ def test_conv_act_matches_conv_bias_relu(cl, dtype, cin, cout, k, stride):
         (y * go).sum().backward()
         (ref * go).sum().backward()
         assert_close(npy(a.grad), npy(b.grad), what="conv_act grad", **tol)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 55, 64), (1, 96, 23, 31), (2, 128, 7, 9)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_instance_norm_half_input_matches_autocast_semantics(shape, relu):
+    """GMA's fp16-autocast encoder: the convolution output is fp16, autocast runs F.instance_norm in fp32 on it and returns
+    fp32; the gradient returns to the convolution in fp16.  The *_h kernels read the fp16 tensor directly."""
+    import torch.nn.functional as F
+    from pcfa_b200.instance_norm import instance_norm
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g) * 3 + 1.5).half().cuda().contiguous(memory_format=torch.channels_last)
+    go = torch.randn(shape, generator=g).cuda()
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = instance_norm(xa, eps=1e-5, relu=relu)
+    assert ya.dtype == torch.float32 and ya.is_contiguous(memory_format=torch.channels_last)
+    yb = F.instance_norm(xb.float(), eps=1e-5)
+    yb = F.relu(yb) if relu else yb
+    assert_close(npy(ya), npy(yb), what="instance norm (fp16 in)", rtol=1e-5, atol_rms=1e-5)
+    (ya * go).sum().backward()
+    (yb * go).sum().backward()
+    assert xa.grad.dtype == torch.float16
+    assert_close(npy(xa.grad), npy(xb.grad), what="instance norm grad (fp16 out)", rtol=2e-3, atol_rms=2e-3)
