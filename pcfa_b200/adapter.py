@@ -10,6 +10,8 @@ helper_functions/own_models.py (ScaledInputModel :9-88), with two deliberate dif
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -124,7 +126,12 @@ def build_network(net: str, device="cuda", seed: int = 0, weights: str | None = 
                 enc.channels_last = True
         if net == "FlowNet2":                                   # plain conv stacks: NHWC weights make every activation NHWC
             model.to(memory_format=torch.channels_last)             # (closure 15.6 -> 11.7 ms, scripts/cl_experiment.py);
-        # PWCNet is slower that way (5.9 -> 6.7 ms: its dense cats and the NCHW correlation/warp operators dominate)
+        if net == "PWCNet" and os.environ.get("PCFA_PWC_CL", "1") != "0":
+            # round 1 measured plain channels-last weights as slower (5.9 -> 6.7 ms: ATen's channels-last cat, conversions
+            # around the NCHW correlation / warp operators); with the vectorised cat kernel, one conversion per feature level
+            # and the fused convolution epilogue the NHWC path wins (networks/pwcnet.py)
+            model.to(memory_format=torch.channels_last)
+            model.channels_last = True
         if net == "RAFT" and channels_last_update:             # NHWC update block: networks/raft.py, BasicUpdateBlock.forward
             model.update_block.to(memory_format=torch.channels_last)
             model.update_block.channels_last = True

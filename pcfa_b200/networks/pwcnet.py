@@ -81,24 +81,42 @@ class PWCDCNet(nn.Module):
             feats[lvl] = x
         return feats
 
+    def _cat(self, xs):
+        """torch.cat(xs, 1); on the channels-last path one vectorised kernel (ATen's channels-last cat is a slow path)."""
+        if self._cl(xs[0]):
+            from ..gru_ops import cat_channels
+            return cat_channels(list(xs), True)
+        return torch.cat(tuple(xs), 1)
+
+    def _cl(self, x):
+        return bool(getattr(self, "channels_last", False)) and x.is_cuda and x.dtype == torch.float32
+
     def _decode(self, lvl, x):
         for i in range(5):
-            x = torch.cat((getattr(self, f"conv{lvl}_{i}")(x), x), 1)
+            x = self._cat((getattr(self, f"conv{lvl}_{i}")(x), x))
         return x, getattr(self, f"predict_flow{lvl}")(x)
 
     def forward(self, im1, im2):
         im1 = torch.stack((im1[:, 2], im1[:, 1], im1[:, 0]), 1)        # RGB -> BGR (PWCNet.py:232-233)
         im2 = torch.stack((im2[:, 2], im2[:, 1], im2[:, 0]), 1)
+        cl = self._cl(im1)
+        if cl:
+            # NHWC through every convolution (cuDNN's sm_100 kernels are NHWC-only: with NCHW activations it converts around
+            # each of the ~70 convolutions, 1.7 ms of a 5.7 ms closure); the correlation / warp operators take NCHW, so each
+            # feature level is converted once
+            im1 = im1.contiguous(memory_format=torch.channels_last)
+            im2 = im2.contiguous(memory_format=torch.channels_last)
         c1, c2 = self._features(im1), self._features(im2)
-        corr = self.leakyRELU(self.corr(c1[6], c2[6]))
-        x, flow = self._decode(6, corr)
+        nchw = (lambda t: t.contiguous()) if cl else (lambda t: t)
+        corr = self.leakyRELU(self.corr(nchw(c1[6]), nchw(c2[6])))
+        x, flow = self._decode(6, corr.contiguous(memory_format=torch.channels_last) if cl else corr)
         flows = {6: flow}
         for lvl in (5, 4, 3, 2):
             up_flow = getattr(self, f"deconv{lvl + 1}")(flow)
             up_feat = getattr(self, f"upfeat{lvl + 1}")(x)
-            warped = self.warp(c2[lvl], up_flow * _FLOW_SCALE[lvl])
-            corr = self.leakyRELU(self.corr(c1[lvl], warped))
-            x, flow = self._decode(lvl, torch.cat((corr, c1[lvl], up_flow, up_feat), 1))
+            warped = self.warp(nchw(c2[lvl]), nchw(up_flow) * _FLOW_SCALE[lvl])
+            corr = self.leakyRELU(self.corr(nchw(c1[lvl]), warped))
+            x, flow = self._decode(lvl, self._cat((corr, c1[lvl], up_flow, up_feat)))
             flows[lvl] = flow
         x = self.dc_conv4(self.dc_conv3(self.dc_conv2(self.dc_conv1(x))))
         flow2 = flow + self.dc_conv7(self.dc_conv6(self.dc_conv5(x)))

@@ -18,15 +18,26 @@ else:
     from pcfa_b200.adapter import build_network
     from pcfa_b200.networks.weights import synthetic_pair
     net = build_network(name, device=device, seed=0)
-    prs = [synthetic_pair(i, 436, 1024) for i in range(batch)]
+    HW = (375, 1242) if name in ("PWCNet", "FlowNet2") else (436, 1024)
+    prs = [synthetic_pair(i, *HW) for i in range(batch)]
     i1, i2 = torch.cat([p[0] for p in prs]), torch.cat([p[1] for p in prs])
 if fmt == "cl":
     net = net.to(memory_format=torch.channels_last)
-padder, img1, img2 = bench.prepare_on_device(i1.pin_memory(), i2.pin_memory(), device)
-target = torch.zeros(img1.shape[0], 2, 436, 1024, device=device)
-iters = 12 if name == "RAFT" else 6
-fo = J.FusedObjective(lambda a, b: net(a, b, iters=iters, test_mode=True)[1], img1, img2, target, mode=J.BOX_COV, joint=False,
-                      pad=padder.top_left, eps_box=bench.EPS_BOX, scale=255.0, delta_bound=bench.DELTA_BOUND, mu=bench.MU, loss="aee")
+if name in ("RAFT", "GMA"):
+    padder, img1, img2 = bench.prepare_on_device(i1.pin_memory(), i2.pin_memory(), device)
+    target = torch.zeros(img1.shape[0], 2, 436, 1024, device=device)
+    iters = 12 if name == "RAFT" else 6
+    fwd, scale = (lambda a, b: net(a, b, iters=iters, test_mode=True)[1]), 255.0
+else:
+    from pcfa_b200.adapter import compute_flow, model_takes_unit_input, preprocess_img
+    unit = model_takes_unit_input(name)
+    a, b = (i1.to(device), i2.to(device)) if unit else (i1.to(device) / 255., i2.to(device) / 255.)
+    padder, (img1, img2) = preprocess_img(name, a, b)
+    img1, img2 = img1.contiguous(), img2.contiguous()
+    target = torch.zeros(img1.shape[0], 2, *HW, device=device)
+    fwd, scale = (lambda a, b: compute_flow(net, name, a, b, test_mode=True)), (1.0 if unit else 255.0)
+fo = J.FusedObjective(fwd, img1, img2, target, mode=J.BOX_COV, joint=False,
+                      pad=padder.top_left, eps_box=bench.EPS_BOX, scale=scale, delta_bound=bench.DELTA_BOUND, mu=bench.MU, loss="aee")
 w1, w2 = bench.init_vars(img1), bench.init_vars(img2)
 g1, g2 = torch.empty_like(w1), torch.empty_like(w2)
 for _ in range(4):
