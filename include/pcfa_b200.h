@@ -346,6 +346,10 @@ int pcfa_gru_step_combine(const float* gh_a, const float* gh_b, const float* cat
  * torch.channels_last tensors, which ATen runs on a slow path). */
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,
                            pcfa_stream_t stream);
+/* Same for arbitrary channel counts, with zero channels appended up to out_channels (a multiple of 4, >= the sum): the
+ * consumer is a convolution with zero-padded input-channel weights, so cuDNN needs no channel-padding launches. */
+int pcfa_cat_channels_last_pad(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,
+                               int out_channels, pcfa_stream_t stream);
 
 /* --------------------------------------------------------------------------- convex up-sampling
  * RAFT.upsample_flow (models/raft/raft.py:72-83; GMA: models/gma/network.py:59-70): softmax over the 9 taps of the

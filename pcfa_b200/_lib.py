@@ -84,6 +84,7 @@ SIGNATURES = {
     "pcfa_lbfgs_store_pair": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_lbfgs_direction": (c_i, [c_fp] * 8 + [c_i64, c_i, c_i, c_i, c_fp]),
     "pcfa_cat_channels_last": (c_i, [c_fp, c_fp, c_i, c_fp, c_i64, c_fp]),
+    "pcfa_cat_channels_last_pad": (c_i, [c_fp, c_fp, c_i, c_fp, c_i64, c_i, c_fp]),
     "pcfa_softmax_rows_f16_forward": (c_i, [c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_softmax_rows_f16_backward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_convex_upsample_workspace_bytes": (c_i64, [c_i, c_i, c_i]),

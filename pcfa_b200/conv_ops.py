@@ -97,6 +97,26 @@ def padded_out_channels(conv: torch.nn.Conv2d, multiple: int = 8):
     return cache[1], cache[2]
 
 
+def padded_in_channels(conv, cin_padded: int):
+    """Weight of a frozen Conv2d / ConvTranspose2d with zero INPUT channels appended up to cin_padded (its input is a
+    concatenation that cat_channels(pad_to=...) extended with zero channels).  Cached per (module, cin_padded)."""
+    key = (conv.weight.data_ptr(), conv.weight._version, cin_padded)
+    cache = getattr(conv, "_pcfa_padded_in", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            w = conv.weight
+            dim = 0 if isinstance(conv, torch.nn.ConvTranspose2d) else 1
+            extra = cin_padded - w.shape[dim]
+            assert extra >= 0
+            shape = list(w.shape)
+            shape[dim] = extra
+            wp = torch.cat([w, w.new_zeros(shape)], dim)
+            wp = wp.contiguous(memory_format=_CL) if _is_cl(w) else wp.contiguous()
+        cache = (key, wp)
+        conv._pcfa_padded_in = cache
+    return cache[1]
+
+
 def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16", slope: float = 0.0,
              tail=None):
     """act?(conv(x)) with `conv`'s geometry (act = ReLU, or LeakyReLU(slope) for slope > 0); `weight` / `bias` override the
@@ -125,4 +145,8 @@ class ConvLeakyReLU(torch.nn.Sequential):
     submodules.py conv()), evaluated through conv_act when the weights are frozen and the input is a CUDA tensor."""
 
     def forward(self, x):
-        return conv_act(self[0], x, True, slope=float(self[1].negative_slope))
+        conv = self[0]
+        if x.shape[1] != conv.in_channels:          # zero channels appended by cat_channels(pad_to=...): zero-padded weights
+            return conv_act(conv, x, True, weight=padded_in_channels(conv, x.shape[1]), tag="_pcfa_padin16",
+                            slope=float(self[1].negative_slope))
+        return conv_act(conv, x, True, slope=float(self[1].negative_slope))

@@ -98,32 +98,43 @@ def usable(*ts: torch.Tensor) -> bool:
 
 class _CatCL(Function):
     @staticmethod
-    def forward(ctx, *xs):
+    def forward(ctx, pad_to, *xs):
         import ctypes as C
         xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
         _check(*xs, name="cat_channels_last")
         B, _, H, W = xs[0].shape
         cs = [int(x.shape[1]) for x in xs]
-        out = torch.empty((B, sum(cs), H, W), device=xs[0].device, dtype=torch.float32, memory_format=torch.channels_last)
+        total = sum(cs)
+        ctot = total if not pad_to else -(-total // pad_to) * pad_to
+        out = torch.empty((B, ctot, H, W), device=xs[0].device, dtype=torch.float32, memory_format=torch.channels_last)
         ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
         chans = (C.c_int * len(xs))(*cs)
         lib = _lib.load()
         _lib.hint_bytes(2 * 4 * out.numel())
-        _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), len(xs), _lib.ptr(out),
-                                              B * H * W, _lib.stream()), "pcfa_cat_channels_last")
+        if pad_to:
+            _lib.check(lib.pcfa_cat_channels_last_pad(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), len(xs), _lib.ptr(out),
+                                                      B * H * W, ctot, _lib.stream()), "pcfa_cat_channels_last_pad")
+        else:
+            _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), len(xs), _lib.ptr(out),
+                                                  B * H * W, _lib.stream()), "pcfa_cat_channels_last")
         ctx.cs = cs
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return tuple(torch.split(g, ctx.cs, dim=1))
+        return (None,) + tuple(torch.split(g[:, :sum(ctx.cs)] if g.shape[1] != sum(ctx.cs) else g, ctx.cs, dim=1))
 
 
-def cat_channels(xs, channels_last: bool):
-    """torch.cat(xs, dim=1); channels-last inputs (B x C_k x H x W, at most four) go through one vectorised kernel."""
+def cat_channels(xs, channels_last: bool, pad_to: int = 0):
+    """torch.cat(xs, dim=1); channels-last inputs (B x C_k x H x W, at most four) go through one vectorised kernel.
+    pad_to > 0 (a multiple of 4): zero channels are appended so that the channel count is a multiple of pad_to (the consumer
+    convolution gets zero-padded input-channel weights, conv_ops.padded_in_channels)."""
     if channels_last and len(xs) <= 4 and all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 for x in xs):
-        return _CatCL.apply(*xs)
-    return torch.cat(xs, dim=1)
+        return _CatCL.apply(int(pad_to), *xs)
+    y = torch.cat(xs, dim=1)
+    if pad_to and y.shape[1] % pad_to:
+        y = torch.nn.functional.pad(y, (0, 0, 0, 0, 0, (-y.shape[1]) % pad_to))
+    return y
 
 
 _CL = torch.channels_last

@@ -81,12 +81,25 @@ class PWCDCNet(nn.Module):
             feats[lvl] = x
         return feats
 
-    def _cat(self, xs):
-        """torch.cat(xs, 1); on the channels-last path one vectorised kernel (ATen's channels-last cat is a slow path)."""
+    def _cat(self, xs, pad=False):
+        """torch.cat(xs, 1); on the channels-last path one vectorised kernel (ATen's channels-last cat is a slow path).
+        pad=True appends zero channels up to a multiple of 8: the decoder's 213-, 181-, 149-, 117-channel inputs (and every
+        DenseNet concatenation grown from them) otherwise make cuDNN wrap each convolution and data gradient in
+        channel-padding launches (150 per closure, 0.9 ms); the consumers use zero-padded input-channel weights."""
         if self._cl(xs[0]):
             from ..gru_ops import cat_channels
-            return cat_channels(list(xs), True)
+            return cat_channels(list(xs), True, pad_to=8 if pad else 0)
         return torch.cat(tuple(xs), 1)
+
+    def _plain(self, m, x):
+        """A plain Conv2d / ConvTranspose2d of the decoder on a possibly zero-padded input."""
+        if x.shape[1] == m.in_channels:
+            return m(x)
+        from ..conv_ops import padded_in_channels
+        w = padded_in_channels(m, x.shape[1])
+        if isinstance(m, nn.ConvTranspose2d):
+            return nn.functional.conv_transpose2d(x, w, m.bias, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+        return nn.functional.conv2d(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups)
 
     def _cl(self, x):
         return bool(getattr(self, "channels_last", False)) and x.is_cuda and x.dtype == torch.float32
@@ -94,7 +107,7 @@ class PWCDCNet(nn.Module):
     def _decode(self, lvl, x):
         for i in range(5):
             x = self._cat((getattr(self, f"conv{lvl}_{i}")(x), x))
-        return x, getattr(self, f"predict_flow{lvl}")(x)
+        return x, self._plain(getattr(self, f"predict_flow{lvl}"), x)
 
     def forward(self, im1, im2):
         im1 = torch.stack((im1[:, 2], im1[:, 1], im1[:, 0]), 1)        # RGB -> BGR (PWCNet.py:232-233)
@@ -109,14 +122,14 @@ class PWCDCNet(nn.Module):
         c1, c2 = self._features(im1), self._features(im2)
         nchw = (lambda t: t.contiguous()) if cl else (lambda t: t)
         corr = self.leakyRELU(self.corr(nchw(c1[6]), nchw(c2[6])))
-        x, flow = self._decode(6, corr.contiguous(memory_format=torch.channels_last) if cl else corr)
+        x, flow = self._decode(6, self._cat((corr,), pad=True) if cl else corr)
         flows = {6: flow}
         for lvl in (5, 4, 3, 2):
             up_flow = getattr(self, f"deconv{lvl + 1}")(flow)
-            up_feat = getattr(self, f"upfeat{lvl + 1}")(x)
+            up_feat = self._plain(getattr(self, f"upfeat{lvl + 1}"), x)
             warped = self.warp(nchw(c2[lvl]), nchw(up_flow) * _FLOW_SCALE[lvl])
             corr = self.leakyRELU(self.corr(nchw(c1[lvl]), warped))
-            x, flow = self._decode(lvl, self._cat((corr, c1[lvl], up_flow, up_feat)))
+            x, flow = self._decode(lvl, self._cat((corr, c1[lvl], up_flow, up_feat), pad=True))
             flows[lvl] = flow
         x = self.dc_conv4(self.dc_conv3(self.dc_conv2(self.dc_conv1(x))))
         flow2 = flow + self.dc_conv7(self.dc_conv6(self.dc_conv5(x)))
