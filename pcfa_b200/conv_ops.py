@@ -32,9 +32,12 @@ def _dummy_like(shape, dtype, device, cl):
 
 class _ConvBiasAct(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0, tail=None):
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0, tail=None, transposed=None):
         lib = _lib.load()
-        y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
+        if transposed is not None:                   # ConvTranspose2d: `transposed` = its output_padding
+            y = F.conv_transpose2d(x, weight, None, stride, padding, transposed, groups, dilation)
+        else:
+            y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
         cl = _is_cl(y)
         if not (cl or y.is_contiguous()):
             y = y.contiguous()
@@ -51,14 +54,14 @@ class _ConvBiasAct(Function):
         if tail is not None:                         # overwrite the last channels (zero filters there): a cat without the copy
             y[:, y.shape[1] - tail.shape[1]:] = tail
         ctx.save_for_backward(weight, y if relu else None)
-        ctx.meta = (tuple(x.shape), x.dtype, x.device, _is_cl(x) or cl, stride, padding, dilation, groups, bool(relu), float(slope))
+        ctx.meta = (tuple(x.shape), x.dtype, x.device, _is_cl(x) or cl, stride, padding, dilation, groups, bool(relu), float(slope), transposed)
         return y
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         weight, y = ctx.saved_tensors
-        shape, dtype, device, cl, stride, padding, dilation, groups, relu, slope = ctx.meta
+        shape, dtype, device, cl, stride, padding, dilation, groups, relu, slope, transposed = ctx.meta
         if relu:
             g = g.contiguous(memory_format=_CL) if _is_cl(y) else g.contiguous()
             if g.dtype != y.dtype:
@@ -74,8 +77,9 @@ class _ConvBiasAct(Function):
         elif g.dtype != weight.dtype:
             g = g.to(weight.dtype)
         gin = torch.ops.aten.convolution_backward(g, _dummy_like(shape, dtype, device, cl), weight, None, stride, padding, dilation,
-                                                  False, (0, 0), groups, (True, False, False))[0]
-        return gin, None, None, None, None, None, None, None, None, None
+                                                  transposed is not None, (0, 0) if transposed is None else transposed, groups,
+                                                  (True, False, False))[0]
+        return gin, None, None, None, None, None, None, None, None, None, None
 
 
 def padded_out_channels(conv: torch.nn.Conv2d, multiple: int = 8):
@@ -119,7 +123,7 @@ def padded_in_channels(conv, cin_padded: int):
 
 def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bias=None, tag: str = "_pcfa_w16", slope: float = 0.0,
              tail=None):
-    """act?(conv(x)) with `conv`'s geometry (act = ReLU, or LeakyReLU(slope) for slope > 0); `weight` / `bias` override the
+    """act?(conv(x)) with `conv`'s geometry (nn.Conv2d or nn.ConvTranspose2d) (act = ReLU, or LeakyReLU(slope) for slope > 0); `weight` / `bias` override the
     module's (e.g. batch-norm-folded copies).  `tail` ([B, k, H, W], no gradient): written over the LAST k output channels
     (which the caller has given zero filters, see padded_out_channels) — torch.cat([conv_out, tail], 1) without the copy."""
     w = conv.weight if weight is None else weight
@@ -132,21 +136,42 @@ def conv_act(conv: torch.nn.Conv2d, x: torch.Tensor, relu: bool, weight=None, bi
             if x.dtype != torch.float16:
                 x = x.to(torch.float16)
         if x.dtype == w.dtype and x.dtype in (torch.float32, torch.float16):
-            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu, slope, tail)
-    y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+            tr = tuple(conv.output_padding) if isinstance(conv, torch.nn.ConvTranspose2d) else None
+            return _ConvBiasAct.apply(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, relu, slope, tail, tr)
+    if isinstance(conv, torch.nn.ConvTranspose2d):
+        y = F.conv_transpose2d(x, w, b, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+    else:
+        y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
     y = (F.leaky_relu(y, slope) if slope else F.relu(y)) if relu else y
     if tail is not None:
         y = torch.cat([y[:, :y.shape[1] - tail.shape[1]], tail], 1)
     return y
 
 
+def apply_conv(conv, x, act_slope=None):
+    """A (frozen) Conv2d / ConvTranspose2d on an input that cat_channels(pad_to=...) may have extended with zero channels:
+    zero-padded input-channel weights, bias (and LeakyReLU(act_slope) / ReLU for act_slope == 0) as the fused epilogue."""
+    w = padded_in_channels(conv, x.shape[1]) if x.shape[1] != conv.in_channels else None
+    if conv.bias is None:
+        if isinstance(conv, torch.nn.ConvTranspose2d):
+            y = F.conv_transpose2d(x, conv.weight if w is None else w, None, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+        else:
+            y = F.conv2d(x, conv.weight if w is None else w, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return y if act_slope is None else (F.leaky_relu(y, act_slope) if act_slope else F.relu(y))
+    return conv_act(conv, x, act_slope is not None, weight=w, tag="_pcfa_w16" if w is None else "_pcfa_padin16", slope=act_slope or 0.0)
+
+
 class ConvLeakyReLU(torch.nn.Sequential):
-    """nn.Sequential(Conv2d, LeakyReLU(slope)) with the same children and state-dict keys (PWCNet.py:23-28, FlowNet's
-    submodules.py conv()), evaluated through conv_act when the weights are frozen and the input is a CUDA tensor."""
+    """nn.Sequential(Conv2d | ConvTranspose2d, LeakyReLU(slope)) with the same children and state-dict keys (PWCNet.py:23-28,
+    FlowNet's submodules.py conv() / deconv()), evaluated through conv_act when the weights are frozen and the input is a
+    CUDA tensor."""
 
     def forward(self, x):
-        conv = self[0]
-        if x.shape[1] != conv.in_channels:          # zero channels appended by cat_channels(pad_to=...): zero-padded weights
-            return conv_act(conv, x, True, weight=padded_in_channels(conv, x.shape[1]), tag="_pcfa_padin16",
-                            slope=float(self[1].negative_slope))
-        return conv_act(conv, x, True, slope=float(self[1].negative_slope))
+        return apply_conv(self[0], x, float(self[1].negative_slope))
+
+
+class ConvOnly(torch.nn.Sequential):
+    """nn.Sequential(Conv2d) (FlowNet's i_conv) on possibly zero-padded inputs."""
+
+    def forward(self, x):
+        return apply_conv(self[0], x, None)

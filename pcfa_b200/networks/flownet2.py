@@ -8,9 +8,13 @@ The three custom operators — Correlation (FlowNetC.py:26-31), Resample2d x4 an
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn import init
+
+_PAD = os.environ.get("PCFA_FN2_PAD", "1") != "0"
 
 
 def conv(cin, cout, kernel_size=3, stride=1):
@@ -20,7 +24,8 @@ def conv(cin, cout, kernel_size=3, stride=1):
 
 
 def i_conv(cin, cout, kernel_size=3, stride=1, bias=True):
-    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=bias))
+    from ..conv_ops import ConvOnly
+    return ConvOnly(nn.Conv2d(cin, cout, kernel_size=kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=bias))
 
 
 def predict_flow(cin):
@@ -28,8 +33,27 @@ def predict_flow(cin):
 
 
 def deconv(cin, cout):
-    return nn.Sequential(nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True),
+    from ..conv_ops import ConvLeakyReLU
+    return ConvLeakyReLU(nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1, bias=True),
                          nn.LeakyReLU(0.1, inplace=True))
+
+
+def _cat(xs):
+    """torch.cat(xs, 1).  On the GPU (channels-last fp32) one kernel that also appends zero channels up to a multiple of 8:
+    the 1026-, 770-, 473-, 386-, 194-, 162-, 82- and 12-channel concatenations otherwise make cuDNN wrap every consuming
+    convolution and its data gradient in channel-padding launches (202 per closure, 1.4 ms); consumers use zero-padded
+    input-channel weights (conv_ops.apply_conv)."""
+    x0 = xs[0]
+    if x0.is_cuda and x0.dtype == torch.float32 and len(xs) <= 4 and _PAD:
+        from ..gru_ops import cat_channels
+        return cat_channels(list(xs), True, pad_to=8)
+    return torch.cat(tuple(xs), 1)
+
+
+def _pf(m, x):
+    """predict_flow / up-sampling (de)convolutions on a possibly zero-padded input."""
+    from ..conv_ops import apply_conv
+    return apply_conv(m, x, None) if x.is_cuda and _PAD else m(x)
 
 
 def _xavier(mod):
@@ -51,15 +75,15 @@ class _Refinement(nn.Module):
             setattr(self, f"upsampled_flow{a}_to_{b}", nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=up_bias))
 
     def _decode(self, c6, c5, c4, c3, c2):
-        flow6 = self.predict_flow6(c6)
-        cat5 = torch.cat((c5, self.deconv5(c6), self.upsampled_flow6_to_5(flow6)), 1)
-        flow5 = self.predict_flow5(cat5)
-        cat4 = torch.cat((c4, self.deconv4(cat5), self.upsampled_flow5_to_4(flow5)), 1)
-        flow4 = self.predict_flow4(cat4)
-        cat3 = torch.cat((c3, self.deconv3(cat4), self.upsampled_flow4_to_3(flow4)), 1)
-        flow3 = self.predict_flow3(cat3)
-        cat2 = torch.cat((c2, self.deconv2(cat3), self.upsampled_flow3_to_2(flow3)), 1)
-        flow2 = self.predict_flow2(cat2)
+        flow6 = _pf(self.predict_flow6, c6)
+        cat5 = _cat((c5, self.deconv5(c6), _pf(self.upsampled_flow6_to_5, flow6)))
+        flow5 = _pf(self.predict_flow5, cat5)
+        cat4 = _cat((c4, self.deconv4(cat5), _pf(self.upsampled_flow5_to_4, flow5)))
+        flow4 = _pf(self.predict_flow4, cat4)
+        cat3 = _cat((c3, self.deconv3(cat4), _pf(self.upsampled_flow4_to_3, flow4)))
+        flow3 = _pf(self.predict_flow3, cat3)
+        cat2 = _cat((c2, self.deconv2(cat3), _pf(self.upsampled_flow3_to_2, flow3)))
+        flow2 = _pf(self.predict_flow2, cat2)
         return (flow2, flow3, flow4, flow5, flow6) if self.training else (flow2,)
 
 
@@ -83,7 +107,7 @@ class FlowNetC(_Refinement):
         a3 = self.conv3(a2)
         b3 = self.conv3(self.conv2(self.conv1(x[:, 3:])))
         corr = self.corr_activation(self.corr(a3, b3))
-        c3 = self.conv3_1(torch.cat((self.conv_redir(a3), corr), 1))
+        c3 = self.conv3_1(_cat((self.conv_redir(a3), corr)))
         c4 = self.conv4_1(self.conv4(c3))
         c5 = self.conv5_1(self.conv5(c4))
         c6 = self.conv6_1(self.conv6(c5))
@@ -138,15 +162,15 @@ class FlowNetSD(nn.Module):
         c4 = self.conv4_1(self.conv4(c3))
         c5 = self.conv5_1(self.conv5(c4))
         c6 = self.conv6_1(self.conv6(c5))
-        flow6 = self.predict_flow6(c6)
-        cat5 = torch.cat((c5, self.deconv5(c6), self.upsampled_flow6_to_5(flow6)), 1)
-        flow5 = self.predict_flow5(self.inter_conv5(cat5))
-        cat4 = torch.cat((c4, self.deconv4(cat5), self.upsampled_flow5_to_4(flow5)), 1)
-        flow4 = self.predict_flow4(self.inter_conv4(cat4))
-        cat3 = torch.cat((c3, self.deconv3(cat4), self.upsampled_flow4_to_3(flow4)), 1)
-        flow3 = self.predict_flow3(self.inter_conv3(cat3))
-        cat2 = torch.cat((c2, self.deconv2(cat3), self.upsampled_flow3_to_2(flow3)), 1)
-        flow2 = self.predict_flow2(self.inter_conv2(cat2))
+        flow6 = _pf(self.predict_flow6, c6)
+        cat5 = _cat((c5, self.deconv5(c6), _pf(self.upsampled_flow6_to_5, flow6)))
+        flow5 = _pf(self.predict_flow5, self.inter_conv5(cat5))
+        cat4 = _cat((c4, self.deconv4(cat5), _pf(self.upsampled_flow5_to_4, flow5)))
+        flow4 = _pf(self.predict_flow4, self.inter_conv4(cat4))
+        cat3 = _cat((c3, self.deconv3(cat4), _pf(self.upsampled_flow4_to_3, flow4)))
+        flow3 = _pf(self.predict_flow3, self.inter_conv3(cat3))
+        cat2 = _cat((c2, self.deconv2(cat3), _pf(self.upsampled_flow3_to_2, flow3)))
+        flow2 = _pf(self.predict_flow2, self.inter_conv2(cat2))
         return (flow2, flow3, flow4, flow5, flow6) if self.training else (flow2,)
 
 
@@ -167,11 +191,11 @@ class FlowNetFusion(nn.Module):
         c0 = self.conv0(x)
         c1 = self.conv1_1(self.conv1(c0))
         c2 = self.conv2_1(self.conv2(c1))
-        flow2 = self.predict_flow2(c2)
-        cat1 = torch.cat((c1, self.deconv1(c2), self.upsampled_flow2_to_1(flow2)), 1)
-        flow1 = self.predict_flow1(self.inter_conv1(cat1))
-        cat0 = torch.cat((c0, self.deconv0(cat1), self.upsampled_flow1_to_0(flow1)), 1)
-        return self.predict_flow0(self.inter_conv0(cat0))
+        flow2 = _pf(self.predict_flow2, c2)
+        cat1 = _cat((c1, self.deconv1(c2), _pf(self.upsampled_flow2_to_1, flow2)))
+        flow1 = _pf(self.predict_flow1, self.inter_conv1(cat1))
+        cat0 = _cat((c0, self.deconv0(cat1), _pf(self.upsampled_flow1_to_0, flow1)))
+        return _pf(self.predict_flow0, self.inter_conv0(cat0))
 
 
 class FlowNet2(nn.Module):
@@ -199,7 +223,7 @@ class FlowNet2(nn.Module):
     def _refine_input(self, x, flow, resample):
         warped = resample(x[:, 3:], flow)
         err = self.channelnorm(x[:, :3] - warped)
-        return torch.cat((x, warped, flow / self.div_flow, err), dim=1)
+        return _cat((x, warped, flow / self.div_flow, err))
 
     def forward(self, inputs):
         """inputs: [B, 3, 2, H, W] in [0, 255] (ownutilities.py:329-339)."""
