@@ -342,6 +342,21 @@ int pcfa_gru_blend_x_backward_acc(const float* z, const float* q, const float* h
 int pcfa_gru_step_combine(const float* gh_a, const float* gh_b, const float* cat0, const float* cat1, const float* cat2,
                           const float* cat3, float* grad_h, float* grad_m, int C, int Cm, int64_t npix, pcfa_stream_t stream);
 
+/* fp16-storage variants of the whole-step GRU kernels (GMA under fp16 autocast; csrc/gru_half.cu): same argument meaning as the
+ * fp32 entry points above, every tensor __half channels-last, fp32 arithmetic per element, 8-byte aligned pointers. */
+int pcfa_cat2_channels_last_h(const void* a, const void* b, void* out, int Ca, int Cb, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_gates_x_forward_h(const void* zr, const void* addend, const void* h, const void* m, void* z, void* r, void* rhm, int C, int Cm,
+                               int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_blend_x_forward_h(const void* z, const void* q_pre, const void* addend, const void* h, const void* m, void* q, void* h_new,
+                               void* hm, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_gates_x_backward_acc_h(const void* z, const void* r, const void* h, const void* grad_z, const void* grad_rhm, void* grad_zr,
+                                    void* grad_h, void* acc, int acc_mode, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_blend_x_backward_acc_h(const void* z, const void* q, const void* h, const void* grad_h_new_a, const void* grad_h_new_b,
+                                    const void* grad_hm, void* grad_z, void* grad_q_pre, void* grad_h, void* acc, int acc_mode, int C, int Cm,
+                                    int64_t npix, pcfa_stream_t stream);
+int pcfa_gru_step_combine_h(const void* gh_a, const void* gh_b, const void* cat0, const void* cat1, const void* cat2, const void* cat3,
+                            void* grad_h, void* grad_m, int C, int Cm, int64_t npix, pcfa_stream_t stream);
+
 /* Channel concatenation of up to four channels-last tensors [npix][C_k] -> [npix][sum C_k] (torch.cat(dim=1) of
  * torch.channels_last tensors, which ATen runs on a slow path). */
 int pcfa_cat_channels_last(const float* const* inputs, const int* channels, int n_inputs, float* out, int64_t npix,

@@ -76,6 +76,12 @@ SIGNATURES = {
     "pcfa_gru_step_combine": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
     "pcfa_bias_act_forward": (c_i, [c_fp, c_fp, c_i64, c_i, c_i64, c_i, c_f, c_i, c_fp]),
     "pcfa_relu_mask_backward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_f, c_i, c_fp]),
+    "pcfa_cat2_channels_last_h": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_gates_x_forward_h": (c_i, [c_fp] * 7 + [c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_blend_x_forward_h": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_gates_x_backward_acc_h": (c_i, [c_fp] * 8 + [c_i, c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_blend_x_backward_acc_h": (c_i, [c_fp] * 10 + [c_i, c_i, c_i, c_i64, c_fp]),
+    "pcfa_gru_step_combine_h": (c_i, [c_fp] * 8 + [c_i, c_i, c_i64, c_fp]),
     "pcfa_lbfgs_workspace_bytes": (c_i64, []),
     "pcfa_lbfgs_update_history": (c_i, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_lbfgs_compact_workspace_bytes": (c_i64, [c_i]),

@@ -233,9 +233,14 @@ class _HoistSource(Function):
 
 
 def hoist_sources(hoist):
-    """[(W_zr, P_zr, W_q, P_q, pad)] x 2 -> the same with P wrapped by _HoistSource, plus the accumulators."""
+    """[(W_zr, P_zr, W_q, P_q, pad)] x 2 -> the same with P wrapped by _HoistSource, plus the accumulators.  Under fp16
+    autocast (GMA) the addends are half: the frozen weights are cast once here instead of by every convolution call."""
     out = []
     for (wzr, pzr, wq, pq, pad) in hoist:
+        pzr, pq = pzr.contiguous(memory_format=_CL), pq.contiguous(memory_format=_CL)
+        if pzr.dtype == torch.float16:
+            wzr = wzr.to(torch.float16).contiguous(memory_format=_CL)
+            wq = wq.to(torch.float16).contiguous(memory_format=_CL)
         azr, aq = torch.empty_like(pzr), torch.empty_like(pq)
         out.append((wzr, _HoistSource.apply(pzr, azr), wq, _HoistSource.apply(pq, aq), pad, azr, aq))
     return out
@@ -247,7 +252,7 @@ _DGRAD_DUMMY = {}
 def _dgrad(gout, weight, in_channels, pad):
     """Data gradient of a stride-1 convolution with frozen weights (channels-last): cuDNN dgrad, nothing else."""
     B, _, H, W = gout.shape
-    key = (gout.device, B, in_channels, H, W)
+    key = (gout.device, gout.dtype, B, in_channels, H, W)
     dummy = _DGRAD_DUMMY.get(key)
     if dummy is None:                                  # only its sizes / memory format are read
         dummy = torch.empty((B, in_channels, H, W), device=gout.device, dtype=gout.dtype, memory_format=_CL)
@@ -262,32 +267,39 @@ class _GRUStepX(Function):
         import ctypes as C
         import torch.nn.functional as F
         lib, P, s = _lib.load(), _lib.ptr, _lib.stream()
-        h, m = h.contiguous(memory_format=_CL), m.contiguous(memory_format=_CL)
-        _check(h, m, pzr1, pq1, pzr2, pq2, name="gru_step_x")
+        dt = pzr1.dtype                                   # fp32 (RAFT) or fp16 (GMA under autocast): one dtype throughout
+        if dt not in (torch.float32, torch.float16) or not h.is_cuda:
+            raise RuntimeError("gru_step_x: expected CUDA float32 / float16 tensors (pcfa_b200 has no CPU path)")
+        sfx = "_h" if dt == torch.float16 else ""
+        h, m = h.to(dt).contiguous(memory_format=_CL), m.to(dt).contiguous(memory_format=_CL)
         B, Ch, H, W = h.shape
         Cm = m.shape[1]
         npix = B * H * W
 
         def new(c):
-            return torch.empty((B, c, H, W), device=h.device, dtype=torch.float32, memory_format=_CL)
+            return torch.empty((B, c, H, W), device=h.device, dtype=dt, memory_format=_CL)
         hm = new(Ch + Cm)
-        ptrs = (C.c_void_p * 2)(h.data_ptr(), m.data_ptr())
-        chans = (C.c_int * 2)(Ch, Cm)
-        _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), 2, P(hm), npix, s), "pcfa_cat_channels_last")
+        if sfx:
+            _lib.check(lib.pcfa_cat2_channels_last_h(P(h), P(m), P(hm), Ch, Cm, npix, s), "pcfa_cat2_channels_last_h")
+        else:
+            ptrs = (C.c_void_p * 2)(h.data_ptr(), m.data_ptr())
+            chans = (C.c_int * 2)(Ch, Cm)
+            _lib.check(lib.pcfa_cat_channels_last(C.cast(ptrs, C.c_void_p), C.cast(chans, C.c_void_p), 2, P(hm), npix, s), "pcfa_cat_channels_last")
+        gates_fwd, blend_fwd = getattr(lib, "pcfa_gru_gates_x_forward" + sfx), getattr(lib, "pcfa_gru_blend_x_forward" + sfx)
         saved = []
         hin = h
         for (wzr, pzr, wq, pq, pad, last) in ((wzr1, pzr1, wq1, pq1, pad1, False), (wzr2, pzr2, wq2, pq2, pad2, True)):
             zr = F.conv2d(hm, wzr, None, 1, pad)
             z, r, rhm = new(Ch), new(Ch), new(Ch + Cm)
-            _lib.check(lib.pcfa_gru_gates_x_forward(P(zr), P(pzr), P(hin), P(m), P(z), P(r), P(rhm), Ch, Cm, npix, s), "pcfa_gru_gates_x_forward")
+            _lib.check(gates_fwd(P(zr), P(pzr), P(hin), P(m), P(z), P(r), P(rhm), Ch, Cm, npix, s), "pcfa_gru_gates_x_forward" + sfx)
             qp = F.conv2d(rhm, wq, None, 1, pad)
             q, hn = new(Ch), new(Ch)
             hm = None if last else new(Ch + Cm)
-            _lib.check(lib.pcfa_gru_blend_x_forward(P(z), P(qp), P(pq), P(hin), P(m), P(q), P(hn), P(hm), Ch, Cm, npix, s), "pcfa_gru_blend_x_forward")
+            _lib.check(blend_fwd(P(z), P(qp), P(pq), P(hin), P(m), P(q), P(hn), P(hm), Ch, Cm, npix, s), "pcfa_gru_blend_x_forward" + sfx)
             saved += [z, r, q, hin]
             hin = hn
         ctx.save_for_backward(*saved, wzr1, wq1, wzr2, wq2)
-        ctx.pads, ctx.accs, ctx.acc_mode, ctx.cm = (pad1, pad2), accs, int(acc_mode), Cm
+        ctx.pads, ctx.accs, ctx.acc_mode, ctx.cm, ctx.sfx = (pad1, pad2), accs, int(acc_mode), Cm, sfx
         return hin
 
     @staticmethod
@@ -297,30 +309,33 @@ class _GRUStepX(Function):
         (pad1, pad2), (azr1, aq1, azr2, aq2), mode, Cm = ctx.pads, ctx.accs, ctx.acc_mode, ctx.cm
         B, Ch, H, W = h0.shape
         npix = B * H * W
-        gh2 = gh2.contiguous(memory_format=_CL)
+        sfx = ctx.sfx
+        gh2 = gh2.to(h0.dtype).contiguous(memory_format=_CL)
+        blend_bwd, gates_bwd = getattr(lib, "pcfa_gru_blend_x_backward_acc" + sfx), getattr(lib, "pcfa_gru_gates_x_backward_acc" + sfx)
+        combine = getattr(lib, "pcfa_gru_step_combine" + sfx)
 
         def new(c):
-            return torch.empty((B, c, H, W), device=h0.device, dtype=torch.float32, memory_format=_CL)
+            return torch.empty((B, c, H, W), device=h0.device, dtype=h0.dtype, memory_format=_CL)
         # ---- vertical half step (second)
         gz, gq, gh1_a = new(Ch), new(Ch), new(Ch)
-        _lib.check(lib.pcfa_gru_blend_x_backward_acc(P(z2), P(q2), P(h1), P(gh2), None, None, P(gz), P(gq), P(gh1_a), P(aq2), mode,
+        _lib.check(blend_bwd(P(z2), P(q2), P(h1), P(gh2), None, None, P(gz), P(gq), P(gh1_a), P(aq2), mode,
                                                      Ch, Cm, npix, s), "pcfa_gru_blend_x_backward_acc")
         grhm2 = _dgrad(gq, wq2, Ch + Cm, pad2)
         gzr, gh1_b = new(2 * Ch), new(Ch)
-        _lib.check(lib.pcfa_gru_gates_x_backward_acc(P(z2), P(r2), P(h1), P(gz), P(grhm2), P(gzr), P(gh1_b), P(azr2), mode, Ch, Cm, npix, s),
+        _lib.check(gates_bwd(P(z2), P(r2), P(h1), P(gz), P(grhm2), P(gzr), P(gh1_b), P(azr2), mode, Ch, Cm, npix, s),
                    "pcfa_gru_gates_x_backward_acc")
         ghm2 = _dgrad(gzr, wzr2, Ch + Cm, pad2)
         # ---- horizontal half step (first): grad of h1 = gh1_a + gh1_b + ghm2[:, :C]
         gz, gq, gh0_a = new(Ch), new(Ch), new(Ch)
-        _lib.check(lib.pcfa_gru_blend_x_backward_acc(P(z1), P(q1), P(h0), P(gh1_a), P(gh1_b), P(ghm2), P(gz), P(gq), P(gh0_a), P(aq1), mode,
+        _lib.check(blend_bwd(P(z1), P(q1), P(h0), P(gh1_a), P(gh1_b), P(ghm2), P(gz), P(gq), P(gh0_a), P(aq1), mode,
                                                      Ch, Cm, npix, s), "pcfa_gru_blend_x_backward_acc")
         grhm1 = _dgrad(gq, wq1, Ch + Cm, pad1)
         gzr, gh0_b = new(2 * Ch), new(Ch)
-        _lib.check(lib.pcfa_gru_gates_x_backward_acc(P(z1), P(r1), P(h0), P(gz), P(grhm1), P(gzr), P(gh0_b), P(azr1), mode, Ch, Cm, npix, s),
+        _lib.check(gates_bwd(P(z1), P(r1), P(h0), P(gz), P(grhm1), P(gzr), P(gh0_b), P(azr1), mode, Ch, Cm, npix, s),
                    "pcfa_gru_gates_x_backward_acc")
         ghm1 = _dgrad(gzr, wzr1, Ch + Cm, pad1)
         gh, gm = new(Ch), new(Cm)
-        _lib.check(lib.pcfa_gru_step_combine(P(gh0_a), P(gh0_b), P(ghm1), P(grhm1), P(grhm2), P(ghm2), P(gh), P(gm), Ch, Cm, npix, s),
+        _lib.check(combine(P(gh0_a), P(gh0_b), P(ghm1), P(grhm1), P(grhm2), P(ghm2), P(gh), P(gm), Ch, Cm, npix, s),
                    "pcfa_gru_step_combine")
         ctx.accs = None
         return (gh, gm) + (None,) * 12

@@ -8,6 +8,8 @@ upsampling only run for the prediction that test_mode returns.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 from torch import einsum
@@ -101,12 +103,19 @@ class GMAUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(256, 64 * 9, 1))
         self.aggregator = Aggregate(dim=128, dim_head=128, heads=num_heads)
 
-    def forward(self, net, inp, corr, flow, attention, want_mask=True, raw_mask=False):
+    def forward(self, net, inp, corr, flow, attention, want_mask=True, raw_mask=False, step_sources=None, last=False):
         """With channels-last inputs (and channels-last weights, adapter.build_network) every tensor stays NHWC: cuDNN's
-        sm_100 kernels are NHWC-only and otherwise convert around each of the ~17 convolutions per iteration."""
+        sm_100 kernels are NHWC-only and otherwise convert around each of the ~17 convolutions per iteration.
+        step_sources (gru_ops.hoist_sources): the whole SepConvGRU step as one autograd node with the context features'
+        share of its convolutions hoisted out of the iteration loop (fp16 kernels under autocast, csrc/gru_half.cu)."""
         motion = self.encoder(flow, corr)
         motion_global = self.aggregator(attention, motion)
-        net = self.gru(net, torch.cat([inp, motion, motion_global], dim=1))
+        if step_sources is not None:
+            from ..gru_ops import gru_step_x
+            dt = step_sources[0][1].dtype
+            net = gru_step_x(net, torch.cat([motion.to(dt), motion_global.to(dt)], dim=1), step_sources, last)
+        else:
+            net = self.gru(net, torch.cat([inp, motion, motion_global], dim=1))
         delta_flow = self.flow_head(net)
         mask = None
         if want_mask:
@@ -161,9 +170,15 @@ class RAFTGMA(nn.Module):
         from ..corr_block import CorrBlock as _OwnCorrBlock
         cl = (bool(getattr(self.update_block, "channels_last", False)) and dev_type == "cuda"
               and isinstance(corr_fn, _OwnCorrBlock))
+        step_sources = None
         if cl:
             net = net.contiguous(memory_format=torch.channels_last)
             inp = inp.contiguous(memory_format=torch.channels_last)
+            frozen = not any(p.requires_grad for p in self.update_block.gru.parameters())
+            if frozen and torch.is_grad_enabled() and os.environ.get("PCFA_GRU_STEP", "1") != "0":
+                from ..gru_ops import hoist_sources
+                with torch.autocast(dev_type, enabled=amp):
+                    step_sources = hoist_sources(self.update_block.gru.hoisted(inp))
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
@@ -171,7 +186,8 @@ class RAFTGMA(nn.Module):
             need_up = (not test_mode) or itr == iters - 1
             with torch.autocast(dev_type, enabled=amp):
                 fl = flow.contiguous(memory_format=torch.channels_last) if cl else flow
-                net, up_mask, delta_flow = self.update_block(net, inp, corr, fl, attention, want_mask=need_up, raw_mask=cl)
+                net, up_mask, delta_flow = self.update_block(net, inp, corr, fl, attention, want_mask=need_up, raw_mask=cl,
+                                                             step_sources=step_sources, last=itr == iters - 1)
             coords1 = coords1 + delta_flow.float().contiguous()
             if need_up:
                 if cl:                                 # fused kernel on the raw mask (csrc/upsample.cu), fp32 like the reference's

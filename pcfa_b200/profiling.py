@@ -58,6 +58,28 @@ def call_bytes(name: str, args):
         return 4 * 5 * args[5]
     if name == "pcfa_gru_blend_backward":                # (z, q, h, ghn, gz, gq, gh, numel, ...): read 4, write 3
         return 4 * 7 * args[7]
+    if name == "pcfa_gru_gates_x_backward_acc":          # (z, r, h, gz, grhm, gzr, gh, acc, mode, C, Cm, npix): + RMW of the accumulator
+        return 4 * args[11] * (8 + (4 if args[8] == 2 else 2 if args[8] == 1 else 0)) * args[9]
+    if name == "pcfa_gru_blend_x_backward_acc":          # (z, q, h, ga, gb, ghm, gz, gq, gh, acc, mode, C, Cm, npix)
+        n, C = args[13], args[11]
+        return 4 * n * C * (3 + 1 + (1 if args[4] is not None else 0) + (1 if args[5] is not None else 0) + 3 + (2 if args[10] == 2 else 1 if args[10] == 1 else 0))
+    if name == "pcfa_gru_step_combine":                  # (gh_a, gh_b, c0..c3, gh, gm, C, Cm, npix): read 2C + C + 4Cm, write C + Cm
+        C, Cm, n = args[8], args[9], args[10]
+        return 4 * n * (4 * C + 5 * Cm)
+    if name == "pcfa_bias_act_forward":                  # (x, bias, n, C, inner, relu, slope, dtype): in place
+        return args[2] * 2 * (4 if args[7] == 0 else 2)
+    if name == "pcfa_relu_mask_backward":                # (y, gy, gx, n, slope, dtype)
+        return args[3] * 3 * (4 if args[5] == 0 else 2)
+    if name == "pcfa_convex_upsample_forward":           # (flow, mask, up, N, H, W, ...): mask 576 + flow 2 in, 128 out per coarse pixel
+        return 4 * args[3] * args[4] * args[5] * (576 + 2 + 128)
+    if name == "pcfa_convex_upsample_backward":          # (flow, mask, gup, gflow, gmask, ws, wsb, N, H, W, ...): mask, gup in; gmask, gflow out
+        return 4 * args[7] * args[8] * args[9] * (576 + 128 + 576 + 2 + 2 + 36)
+    if name == "pcfa_cat_channels_last_pad":             # (inputs, channels, n, out, npix, out_channels)
+        return 2 * 4 * args[4] * args[5]
+    if name == "pcfa_softmax_rows_f16_forward":          # (sim, attn, rows, cols)
+        return 2 * 2 * args[2] * args[3]
+    if name == "pcfa_softmax_rows_f16_backward":         # (attn, gattn, gsim, rows, cols)
+        return 3 * 2 * args[3] * args[4]
     if name == "pcfa_instnorm_forward":                  # (x, y, stats, ws, B, C, H, W, ...): read x, write y
         return 4 * 2 * args[4] * args[5] * args[6] * args[7]
     if name == "pcfa_instnorm_backward":                 # (x, gy, stats, gx, ws, B, C, H, W, ...): read x, gy, write gx

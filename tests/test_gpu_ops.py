@@ -541,3 +541,39 @@ def test_instance_norm_half_input_matches_autocast_semantics(shape, relu):
     (yb * go).sum().backward()
     assert xa.grad.dtype == torch.float16
     assert_close(npy(xa.grad), npy(xb.grad), what="instance norm grad (fp16 out)", rtol=2e-3, atol_rms=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_gru_step_x_matches_sepconvgru_composition(dtype):
+    """One autograd node per SepConvGRU step (gru_ops.gru_step_x: hoisted context share, fused element-wise kernels,
+    in-kernel gradient sums, accumulated addend gradients) against the module composition of models/raft/update.py:33-60
+    evaluated in fp32 — forward, grad h, grad motion and grad of the context features over TWO chained steps (so the
+    accumulate-over-iterations path of _HoistSource is exercised); fp16 storage variant for GMA's autocast."""
+    from pcfa_b200.gru_ops import gru_step_x, hoist_sources
+    from pcfa_b200.networks.raft import SepConvGRU
+    g = torch.Generator().manual_seed(5)
+    B, Ch, Ci, Cm, H, W = 1, 128, 128, 128, 12, 20
+    gru = SepConvGRU(hidden_dim=Ch, input_dim=Ci + Cm).cuda()
+    for p in gru.parameters():
+        p.requires_grad = False
+    gru.to(memory_format=torch.channels_last)
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)            # noqa: E731
+    h0, inp = cl(torch.tanh(torch.randn(B, Ch, H, W, generator=g))), cl(torch.relu(torch.randn(B, Ci, H, W, generator=g)))
+    m1, m2 = cl(torch.randn(B, Cm, H, W, generator=g)), cl(torch.randn(B, Cm, H, W, generator=g))
+    go = cl(torch.randn(B, Ch, H, W, generator=g))
+    # reference: the module, fp32, twice
+    ra, ri, rm1, rm2 = (t.clone().requires_grad_(True) for t in (h0, inp, m1, m2))
+    ref = gru(gru(ra, torch.cat([ri, rm1], 1)), torch.cat([ri, rm2], 1))
+    (ref * go).sum().backward()
+    # fused
+    a, i_, b1, b2 = (t.clone().to(dtype).requires_grad_(True) for t in (h0, inp, m1, m2))
+    with torch.autocast("cuda", enabled=dtype == torch.float16):
+        src = hoist_sources(gru.hoisted(i_))
+    out = gru_step_x(gru_step_x(a, b1, src, False), b2, src, True)
+    assert out.dtype == dtype
+    (out.float() * go).sum().backward()
+    tol = 2e-3 if dtype == torch.float32 else 3e-2
+    rel = lambda x, y: float((x.float() - y).norm() / y.norm())                      # noqa: E731
+    assert rel(out, ref) < tol, rel(out, ref)
+    for name, got, want in (("h", a.grad, ra.grad), ("m1", b1.grad, rm1.grad), ("m2", b2.grad, rm2.grad), ("inp", i_.grad, ri.grad)):
+        assert rel(got, want) < tol, (name, rel(got, want))
