@@ -573,7 +573,7 @@ def test_gru_step_x_matches_sepconvgru_composition(dtype):
     assert out.dtype == dtype
     (out.float() * go).sum().backward()
     tol = 2e-3 if dtype == torch.float32 else 3e-2
-    rel = lambda x, y: float((x.float() - y).norm() / y.norm())                      # noqa: E731
+    rel = lambda x, y: float((x.detach().float() - y.detach()).norm() / y.detach().norm())      # noqa: E731
     assert rel(out, ref) < tol, rel(out, ref)
     for name, got, want in (("h", a.grad, ra.grad), ("m1", b1.grad, rm1.grad), ("m2", b2.grad, rm2.grad), ("inp", i_.grad, ri.grad)):
         assert rel(got, want) < tol, (name, rel(got, want))
