@@ -10,7 +10,7 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpcfa_b200.so"
+_LIB_PATH = Path(os.environ.get("PCFA_LIB") or (Path(__file__).resolve().parent / "lib" / "libpcfa_b200.so"))   # PCFA_LIB: experiments
 _lib = None
 _raw = None
 _profile = None        # None, or dict: entry point name -> list of (start_event, end_event)

@@ -28,7 +28,11 @@
 namespace pcfa {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
-constexpr int TC_PH = 8, TC_PW = 16;          // target patch
+#ifndef PCFA_TC_PH
+#define PCFA_TC_PH 8
+#define PCFA_TC_PW 16
+#endif
+constexpr int TC_PH = PCFA_TC_PH, TC_PW = PCFA_TC_PW;          // target patch
 constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 384;             // 4 control warps + 8 epilogue warps
 constexpr int TC2_THREADS = 640;            // CTA-pair kernel: 4 control warps + 16 epilogue warps (lane quarter x column quarter)
