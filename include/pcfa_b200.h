@@ -105,6 +105,24 @@ int pcfa_corr_lookup_backward(const float* grad_out, const float* coords,
                               int B, int H, int W, int num_levels, int radius,
                               pcfa_stream_t stream);
 
+/* Sparse backward (no reference counterpart: the reference's autograd materialises and sums one dense 261 MB gradient per
+ * lookup, models/raft/corr.py:29-50).  The lookup windows of all iterations cover only part of the gradient pyramid (29-52 %
+ * of its 32-query x 32-cell blocks at 55x128, profiles/g_sparsity_r2.txt).  `occupancy` is a bitmap of those blocks
+ * (uint32 words [B][ceil(HW/32)][words], pcfa_corr_occupancy_bytes):
+ *   pcfa_corr_occupancy_mark          ONE launch per backward pass: sets the bits of every block the lookups at
+ *                                     coords_list[0..n_lookups) (a HOST array of device pointers, each [B,2,H,W] as passed to
+ *                                     pcfa_corr_lookup_backward[_cl]) may have written; bits are OR-ed in
+ *   pcfa_corr_pyramid_backward_occ    = pcfa_corr_pyramid_backward, reading only marked blocks (tensor-core path; the other
+ *                                     paths ignore the bitmap)
+ * Contract: the caller zero-fills `occupancy` (e.g. together with grad_pyramid) and marks EVERY lookup that accumulated into
+ * grad_pyramid; an unmarked non-zero block is silently dropped. */
+int64_t pcfa_corr_occupancy_bytes(int B, int H, int W, int num_levels);
+int pcfa_corr_occupancy_mark(const float* const* coords_list, int n_lookups, uint32_t* occupancy /* (bits set) */,
+                             int B, int H, int W, int num_levels, int radius, pcfa_stream_t stream);
+int pcfa_corr_pyramid_backward_occ(const float* grad_pyramid, const uint32_t* occupancy, const float* fmap1, const float* fmap2,
+                                   float* grad_fmap1, float* grad_fmap2, void* workspace, int64_t workspace_bytes,
+                                   int B, int C, int H, int W, int num_levels, int impl, pcfa_stream_t stream);
+
 /* ======================================================================================
  * (a5) Spatial correlation sampler — replaces spatial_correlation_sampler_backend.forward /
  *      .backward  (Correlation_Module/correlation_sampler.cpp:58-117, CPU semantics of

@@ -40,6 +40,9 @@ SIGNATURES = {
     "pcfa_corr_lookup_backward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_corr_lookup_forward_cl": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_corr_lookup_backward_cl": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_occupancy_bytes": (c_i64, [c_i, c_i, c_i, c_i]),
+    "pcfa_corr_occupancy_mark": (c_i, [c_fp, c_i, c_fp, c_i, c_i, c_i, c_i, c_i, c_fp]),
+    "pcfa_corr_pyramid_backward_occ": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_scs_output_size": (c_i, [c_i, c_i, C.POINTER(ScsParams), C.POINTER(c_i), C.POINTER(c_i)]),
     "pcfa_scs_forward": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),
     "pcfa_scs_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i, C.POINTER(ScsParams), c_f, c_fp]),

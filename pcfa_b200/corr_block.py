@@ -39,11 +39,21 @@ def _impl_from_env():
 
 class _PyramidState:
     """Per-CorrBlock side state shared by the build and lookup autograd nodes."""
-    __slots__ = ("B", "C", "H", "W", "levels", "total", "grad", "impl")
+    __slots__ = ("B", "C", "H", "W", "levels", "total", "grad", "impl", "occ_words", "lookups")
 
     def __init__(self, B, Cc, H, W, levels, total, impl):
         self.B, self.C, self.H, self.W, self.levels, self.total, self.impl = B, Cc, H, W, levels, total, impl
-        self.grad = None        # persistent gradient pyramid of the current backward pass
+        self.grad = None        # persistent gradient pyramid of the current backward pass, + the occupancy bitmap as its tail
+        self.occ_words = 0      # 32-bit words of the bitmap behind the pyramid in `grad` (0: none)
+        self.lookups = []       # (coords, radius) of every lookup that has accumulated into `grad`
+
+    def new_grad(self, device):
+        """Zeroed gradient pyramid with the occupancy bitmap of the sparse backward behind it: ONE fill clears both."""
+        lib = _lib.load()
+        sparse = os.environ.get("PCFA_BWD_SPARSE", "1") != "0"
+        self.occ_words = (lib.pcfa_corr_occupancy_bytes(self.B, self.H, self.W, self.levels) // 4) if sparse else 0
+        self.lookups = []
+        self.grad = torch.zeros(self.total + self.occ_words, device=device, dtype=torch.float32)
 
 
 class _BuildPyramid(torch.autograd.Function):
@@ -68,22 +78,38 @@ class _BuildPyramid(torch.autograd.Function):
         lib = _lib.load()
         fmap1, fmap2 = ctx.saved_tensors
         st = ctx.state
-        G = st.grad
-        st.grad = None
+        G, lookups = st.grad, st.lookups
+        st.grad, st.lookups = None, []
         if G is None and gpyr is None:
             return None, None, None
+        occ = None
         if G is None:
             G = gpyr.contiguous()
-        elif gpyr is not None:          # someone differentiated through corr_pyramid directly
-            G = G + gpyr
+        elif gpyr is not None:          # someone differentiated through corr_pyramid directly: dense gradient
+            G = G[:st.total] + gpyr
+        elif st.occ_words:
+            # only the lookups wrote into G: mark the 32x32 blocks their windows cover (one launch per radius in use) and let
+            # the build's backward skip the rest (pcfa_b200.h: pcfa_corr_occupancy_mark)
+            occ = G[st.total:]
+            for radius in sorted({r for _, r in lookups}):
+                ptrs = [c.data_ptr() for c, r in lookups if r == radius]
+                arr = (C.c_void_p * len(ptrs))(*ptrs)
+                _lib.check(lib.pcfa_corr_occupancy_mark(arr, len(ptrs), _lib.ptr(occ), st.B, st.H, st.W, st.levels, radius,
+                                                        _lib.stream()), "pcfa_corr_occupancy_mark")
         g1 = torch.empty_like(fmap1)
         g2 = torch.empty_like(fmap2)
         wsb = lib.pcfa_corr_pyramid_workspace_bytes(st.B, st.C, st.H, st.W, st.levels)
         ws = torch.empty(wsb, device=fmap1.device, dtype=torch.uint8)
-        _lib.check(lib.pcfa_corr_pyramid_backward(_lib.ptr(G), _lib.ptr(fmap1), _lib.ptr(fmap2),
-                                                  _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(ws), wsb,
-                                                  st.B, st.C, st.H, st.W, st.levels, st.impl,
-                                                  _lib.stream()), "pcfa_corr_pyramid_backward")
+        if occ is not None:
+            _lib.check(lib.pcfa_corr_pyramid_backward_occ(_lib.ptr(G), _lib.ptr(occ), _lib.ptr(fmap1), _lib.ptr(fmap2),
+                                                          _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(ws), wsb,
+                                                          st.B, st.C, st.H, st.W, st.levels, st.impl,
+                                                          _lib.stream()), "pcfa_corr_pyramid_backward_occ")
+        else:
+            _lib.check(lib.pcfa_corr_pyramid_backward(_lib.ptr(G), _lib.ptr(fmap1), _lib.ptr(fmap2),
+                                                      _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(ws), wsb,
+                                                      st.B, st.C, st.H, st.W, st.levels, st.impl,
+                                                      _lib.stream()), "pcfa_corr_pyramid_backward")
         return g1, g2, None
 
 
@@ -109,11 +135,12 @@ class _Lookup(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         st = ctx.state
         if st.grad is None:
-            st.grad = torch.zeros(st.total, device=gout.device, dtype=torch.float32)
+            st.new_grad(gout.device)
         gout = gout.contiguous(memory_format=torch.channels_last) if ctx.cl else gout.contiguous()
         fn = lib.pcfa_corr_lookup_backward_cl if ctx.cl else lib.pcfa_corr_lookup_backward
         _lib.check(fn(_lib.ptr(gout), _lib.ptr(coords), _lib.ptr(st.grad), st.B, st.H, st.W, st.levels, ctx.radius,
                       _lib.stream()), "pcfa_corr_lookup_backward")
+        st.lookups.append((coords, ctx.radius))
         # the pyramid's gradient travels through st.grad (consumed by _BuildPyramid.backward, which
         # autograd runs after every lookup node); coords are detached in RAFT/GMA (raft.py:123)
         return None, None, None, None, None

@@ -62,4 +62,26 @@ __host__ __device__ inline PyramidLayout make_pyramid_layout(int B, int H, int W
     return L;
 }
 
+// Occupancy bitmap of the gradient pyramid (sparse backward): bit (g, c) of sample b says that some element of
+// G[queries 32g .. 32g+31][cells 32k .. 32k+31 of level l] may be non-zero, with column c = chunk_off[l] + k.
+// Words: [B][qgroups][words] uint32.  Written by the lookup backward (_occ variants), read by the pyramid backward.
+struct OccLayout {
+    int qgroups, chunks, words;      // rows (= ceil(N/32)), columns over all levels, 32-bit words per row
+    int chunk_off[9];
+};
+
+__host__ __device__ inline OccLayout make_occ_layout(int H, int W, int levels) {
+    OccLayout o;
+    o.qgroups = (H * W + 31) / 32;
+    int h = H, w = W, c = 0;
+    for (int l = 0; l < 8; ++l) {
+        o.chunk_off[l] = c;
+        if (l < levels) { c += (h * w + 31) / 32; h /= 2; w /= 2; }
+    }
+    o.chunk_off[8] = c;
+    o.chunks = c;
+    o.words = (c + 31) / 32;
+    return o;
+}
+
 }  // namespace pcfa

@@ -16,7 +16,7 @@ int64_t corr_pyramid_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_tc_supported(int B, int C, int H, int W, int levels);
 // --- tcgen05 backward (corr_allpairs_bwd_tc.cu) ----------------------------------------------
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
-                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta);
+                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta, const unsigned* occ);
 int64_t corr_pyramid_bwd_tc_workspace_bytes(int B, int C, int H, int W, int levels);
 bool corr_pyramid_bwd_tc_supported(int B, int C, int H, int W, int levels);
 
@@ -195,7 +195,7 @@ extern "C" int pcfa_corr_pyramid_forward(const float* fmap1, const float* fmap2,
     return forward_simt(fmap1, fmap2, pyramid, B, C, H, W, num_levels, as_stream(stream));
 }
 
-extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float* fmap1,
+static int pyramid_backward(const float* grad_pyramid, const unsigned* occ, const float* fmap1,
                                           const float* fmap2, float* grad_fmap1, float* grad_fmap2,
                                           void* workspace, int64_t workspace_bytes, int B, int C,
                                           int H, int W, int num_levels, int impl,
@@ -208,11 +208,28 @@ extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float
         if (!workspace || workspace_bytes < corr_pyramid_bwd_tc_workspace_bytes(B, C, H, W, num_levels))
             return PCFA_E_WORKSPACE;
         return corr_pyramid_backward_tc(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace,
-                                        workspace_bytes, B, C, H, W, num_levels, as_stream(stream), impl == 2 ? 0 : 1);
+                                        workspace_bytes, B, C, H, W, num_levels, as_stream(stream), impl == 2 ? 0 : 1, occ);
     }
     const int64_t need = 2 * pooled_floats(B, C, H, W, num_levels) * (int64_t)sizeof(float);
     if (need > 0 && (!workspace || workspace_bytes < need)) return PCFA_E_WORKSPACE;
     return backward_simt(grad_pyramid, fmap1, fmap2, grad_fmap1, grad_fmap2,
                          reinterpret_cast<float*>(workspace), B, C, H, W, num_levels,
                          as_stream(stream));
+}
+
+extern "C" int pcfa_corr_pyramid_backward(const float* grad_pyramid, const float* fmap1, const float* fmap2, float* grad_fmap1,
+                                          float* grad_fmap2, void* workspace, int64_t workspace_bytes, int B, int C, int H,
+                                          int W, int num_levels, int impl, pcfa_stream_t stream) {
+    return pyramid_backward(grad_pyramid, nullptr, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace, workspace_bytes, B, C, H, W,
+                            num_levels, impl, stream);
+}
+// Sparse variant: `occupancy` (pcfa_corr_lookup_backward_cl_occ) names the 32x32 blocks of grad_pyramid that may be non-zero;
+// the tensor-core CTA-pair path skips every K-chunk without marked blocks, the other paths ignore the bitmap (dense).
+extern "C" int pcfa_corr_pyramid_backward_occ(const float* grad_pyramid, const uint32_t* occupancy, const float* fmap1,
+                                              const float* fmap2, float* grad_fmap1, float* grad_fmap2, void* workspace,
+                                              int64_t workspace_bytes, int B, int C, int H, int W, int num_levels, int impl,
+                                              pcfa_stream_t stream) {
+    if (!occupancy || (reinterpret_cast<uintptr_t>(occupancy) & 3)) return PCFA_E_BADARG;
+    return pyramid_backward(grad_pyramid, occupancy, fmap1, fmap2, grad_fmap1, grad_fmap2, workspace, workspace_bytes, B, C, H, W,
+                            num_levels, impl, stream);
 }

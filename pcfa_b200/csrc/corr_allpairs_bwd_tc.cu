@@ -45,9 +45,13 @@ struct BwParams {
     int unit_off[BW_MAX_LEVELS + 1];     // pass II: block-pair prefix over levels
     float* out[BW_MAX_LEVELS];           // pass I: out[0] = grad_fmap1 ; pass II: grad of P_l (out[0] = grad_fmap2)
     unsigned long long* trace;           // optional per-CTA timeline (8 globaltimer stamps), set by pcfa_debug_set_trace
+    // sparse mode (CTA-pair kernel, occupancy bitmap given): the K-chunks of a unit are the set bits of its live mask
+    int sparse, det, nunits, mask_words; // nunits = B * units_per_sample
+    const unsigned* wl_mask;             // [nunits][mask_words]  bit k: K-chunk k of the unit has marked blocks
+    const int* wl_cnt;                   // [nunits]              popcount of the mask
 };
 
-struct BwSegment { int b, level, rows_total, m0a, m0b, nblk, k0, k1; long long next; };
+struct BwSegment { int b, level, rows_total, m0a, m0b, nblk, k0, k1, ug; long long next; };
 
 // The CTA's share [w, w_end) of the linear work space is cut at unit boundaries into segments; every warp role
 // walks the same segments.
@@ -223,12 +227,25 @@ __device__ __forceinline__ void bw_stamp(unsigned long long* tr, int slot) {
 constexpr int BW2_MAX_STAGES = 4;
 constexpr int BW2_STG_BYTES = 32 * BW_BM * 4;     // epilogue staging tile for the bulk reduce-add
 
-__device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, const BwParams& P, int rank) {
+// Walks the CTA pair's share of the linear (unit, K-chunk) space.  Dense: every unit has chunks_total chunks.  Sparse: unit
+// ug has the live chunks [pre[ug], pre[ug+1]) (prefix sums of wl_cnt in shared memory); k0/k1 are then ORDINALS among the
+// unit's live chunks, which the TMA producer maps to chunk indices by walking the set bits of the unit's mask.
+__device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, const BwParams& P, int rank, const int* pre,
+                                                 int& cursor) {
     BwSegment sg;
-    const long long ug = w / P.chunks_total;
-    sg.k0 = (int)(w - ug * P.chunks_total);
-    const long long unit_end = (ug + 1) * P.chunks_total;
-    sg.next = unit_end < w_end ? unit_end : w_end;
+    long long ug;
+    if (P.sparse) {
+        while (pre[cursor + 1] <= w) ++cursor;
+        ug = cursor;
+        sg.k0 = (int)(w - pre[cursor]);
+        const long long unit_end = pre[cursor + 1];
+        sg.next = unit_end < w_end ? unit_end : w_end;
+    } else {
+        ug = w / P.chunks_total;
+        sg.k0 = (int)(w - ug * P.chunks_total);
+        const long long unit_end = (ug + 1) * P.chunks_total;
+        sg.next = unit_end < w_end ? unit_end : w_end;
+    }
     sg.k1 = sg.k0 + (int)(sg.next - w);
     sg.b = (int)(ug / P.units_per_sample);
     const int unit = (int)(ug - (long long)sg.b * P.units_per_sample);
@@ -244,6 +261,7 @@ __device__ __forceinline__ BwSegment bw2_segment(long long w, long long w_end, c
     sg.m0a = (quad * 4 + rank * 2) * BW_BM;          // this CTA's two row blocks (may lie past rows_total: zero-filled)
     sg.m0b = sg.m0a + BW_BM;
     sg.nblk = 2;
+    sg.ug = (int)ug;
     return sg;
 }
 
@@ -259,10 +277,10 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
     const uint32_t bar_full = bars, bar_empty = bars + 8 * BW2_MAX_STAGES;
     const uint32_t bar_accfull = bar_empty + 8 * BW2_MAX_STAGES, bar_accempty = bar_accfull + 8;
     const uint32_t tmem_slot = bar_accempty + 8;
+    int* pre = reinterpret_cast<int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));     // sparse: [nunits + 1] prefix sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const long long ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
-    const long long w_begin = P.work_total * cid / ncl, w_end = P.work_total * (cid + 1) / ncl;
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * P.C) tmem_cols <<= 1;
 
@@ -281,19 +299,50 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
+    if (P.sparse && warp == 3) {                                        // prefix sums of the units' live-chunk counts
+        int run = 0;
+        for (int u0 = 0; u0 < P.nunits; u0 += 32) {
+            int v = (u0 + lane < P.nunits) ? P.wl_cnt[u0 + lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+            if (u0 + lane < P.nunits) pre[u0 + lane + 1] = run + v;
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) pre[0] = 0;
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) bw_stamp(P.trace, 1);
+    // this pair's share: equal counts of (live) chunks; deterministic mode cuts at unit boundaries (one RED.ADD per output)
+    long long w_begin, w_end;
+    if (P.sparse) {
+        if (P.det) { w_begin = pre[(long long)P.nunits * cid / ncl]; w_end = pre[(long long)P.nunits * (cid + 1) / ncl]; }
+        else { const long long total = pre[P.nunits]; w_begin = total * cid / ncl; w_end = total * (cid + 1) / ncl; }
+    } else { w_begin = P.work_total * cid / ncl; w_end = P.work_total * (cid + 1) / ncl; }
 
     if (warp == 0 && lane == 0) {
         // ===================================================================== TMA producer (both CTAs)
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0, cursor = 0; uint32_t phase = 0;
         for (long long w = w_begin; w < w_end;) {
-            const BwSegment sg = bw2_segment(w, w_end, P, rank);
-            for (int kc = sg.k0; kc < sg.k1; ++kc) {
+            const BwSegment sg = bw2_segment(w, w_end, P, rank, pre, cursor);
+            const unsigned* mk = P.wl_mask + (size_t)sg.ug * P.mask_words;
+            int wi = 0; unsigned live = 0;
+            if (P.sparse) {                                         // position on the k0-th set bit of the unit's mask
+                int skip = sg.k0;
+                live = __ldg(mk);
+                for (int c = __popc(live); skip >= c; c = __popc(live)) { skip -= c; live = __ldg(mk + ++wi); }
+                while (skip-- > 0) live &= live - 1;
+            }
+            for (int ord = sg.k0; ord < sg.k1; ++ord) {
+                int kc = ord;
+                if (P.sparse) {
+                    while (!live) live = __ldg(mk + ++wi);
+                    kc = wi * 32 + __ffs(live) - 1;
+                    live &= live - 1;
+                }
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t dst = base + stage * stage_bytes;
                 const uint32_t full = leader_bar(bar_full + 8 * stage);
@@ -326,9 +375,9 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
         // ===================================================================== MMA issuer (leader only)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((P.pass == 2 ? 1u : 0u) << 15) |
                                ((uint32_t)(P.C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-        int stage = 0; uint32_t phase = 0, accphase = 0;
+        int stage = 0, cursor = 0; uint32_t phase = 0, accphase = 0;
         for (long long w = w_begin; w < w_end;) {
-            const BwSegment sg = bw2_segment(w, w_end, P, 0);
+            const BwSegment sg = bw2_segment(w, w_end, P, 0, pre, cursor);
             mbar_wait(bar_accempty, accphase ^ 1);
             tc_fence_after();
             for (int kc = sg.k0; kc < sg.k1; ++kc) {
@@ -365,8 +414,9 @@ corr_pyramid_bwd_tc2_kernel(const __grid_constant__ BwMaps maps, const BwParams 
         const uint32_t my_stg = stg + r * BW2_STG_BYTES;
         const bool issuer = (ew == 0 && lane == 0);
         uint32_t accphase = 0, gg = 0;
+        int cursor = 0;
         for (long long w = w_begin; w < w_end;) {
-            const BwSegment sg = bw2_segment(w, w_end, P, rank);
+            const BwSegment sg = bw2_segment(w, w_end, P, rank, pre, cursor);
             mbar_wait(bar_accfull, accphase);
             tc_fence_after();
             if (warp == 4 && lane == 0) bw_stamp(P.trace, sg.next >= w_end ? 5 : 4);
@@ -429,6 +479,11 @@ struct BwPrepArgs {
     int h[BW_MAX_LEVELS], w[BW_MAX_LEVELS];
     int levels, B, C, write_lo;
     float alpha;
+    // sparse mode: per-unit live masks of both passes, built from the occupancy bitmap by extra CTAs of the prep launch
+    const unsigned* occ; OccLayout OL;
+    unsigned* mask1; int* cnt1; unsigned* mask2; int* cnt2;
+    int units1, units2, words1, words2;
+    int unit_off2[BW_MAX_LEVELS + 1];
 };
 __device__ __forceinline__ void tf32_split(float v, float* hi, float* lo) {
     uint32_t h;
@@ -455,13 +510,64 @@ __device__ __forceinline__ void bw_prep_drain(const float* __restrict__ t, int c
     }
 }
 
+// One CTA per (sample, unit) of either pass.  Pass I unit u = queries [512u, +512) = bitmap rows [16u, +16): its mask over
+// the K-chunks (32-cell chunks of all levels) is the OR of those rows.  Pass II unit (level l, quad) = cells [512 quad, +512)
+// of level l = bitmap columns [chunk_off[l] + 16 quad, +16): its mask over the K-chunks (32-query groups) has bit g set
+// when row g has any of those columns.
+__device__ __forceinline__ void bw_mask_block(const BwPrepArgs& a, int id) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int per = a.units1 + a.units2;
+    const int b = id / per, u = id - b * per;
+    const unsigned* ob = a.occ + (long long)b * a.OL.qgroups * a.OL.words;
+    int local = 0;
+    if (u < a.units1) {
+        unsigned* mo = a.mask1 + ((long long)b * a.units1 + u) * a.words1;
+        const int g0 = u * 16, g1 = min(g0 + 16, a.OL.qgroups);
+        for (int wi = threadIdx.x; wi < a.words1; wi += 256) {
+            unsigned m = 0;
+            for (int g = g0; g < g1; ++g) m |= __ldg(ob + g * a.OL.words + wi);
+            mo[wi] = m;
+            local += __popc(m);
+        }
+    } else {
+        const int v = u - a.units1;
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < BW_MAX_LEVELS; ++i)
+            if (i < a.levels && v >= a.unit_off2[i]) l = i;
+        const int c0 = a.OL.chunk_off[l] + 16 * (v - a.unit_off2[l]), c1 = min(c0 + 16, a.OL.chunk_off[l + 1]);   // [c0, c1)
+        const int w0 = c0 >> 5, w1 = (c1 - 1) >> 5;
+        const unsigned lo = 0xffffffffu << (c0 & 31), hi = 0xffffffffu >> (31 - ((c1 - 1) & 31));
+        const unsigned mA = (w0 == w1) ? (lo & hi) : lo, mB = (w0 == w1) ? 0u : hi;
+        unsigned* mo = a.mask2 + ((long long)b * a.units2 + v) * a.words2;
+        for (int g = threadIdx.x; g < a.words2 * 32; g += 256) {
+            bool on = false;
+            if (g < a.OL.qgroups) {
+                on = (__ldg(ob + g * a.OL.words + w0) & mA) != 0;
+                if (mB) on = on || (__ldg(ob + g * a.OL.words + w1) & mB) != 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if ((threadIdx.x & 31) == 0) { mo[g >> 5] = bal; local += __popc(bal); }
+        }
+    }
+    if (local) atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (u < a.units1) a.cnt1[b * a.units1 + u] = cnt;
+        else a.cnt2[b * a.units2 + (u - a.units1)] = cnt;
+    }
+}
+
 // blockIdx.x < flat_blocks: elementwise part (fmap1 -> TF32 planes, zero-fill of grad_fmap1 / grad_fmap2), 4 elements
 // per thread (128-bit accesses when `vec`).  Remaining CTAs: BP_CH channels x (8 rows x 32 cols) of fmap2, pooled.
 __global__ void __launch_bounds__(256)
 bw_prep_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const BwPrepArgs a, int flat_blocks, int vec,
-               int nx, int ny) {
+               int nx, int ny, int first_mask_block) {
     const int H = a.h[0], W = a.w[0];
     const long long hw = (long long)H * W;
+    if ((int)blockIdx.x >= first_mask_block) { bw_mask_block(a, (int)blockIdx.x - first_mask_block); return; }
     if ((int)blockIdx.x < flat_blocks) {
         const long long n = (long long)a.B * a.C * hw;
         const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
@@ -575,7 +681,11 @@ bw_unpool_kernel(float* __restrict__ gf2, const BwUnpool a, int H, int W, int ve
     }
 }
 
-struct BwWorkspace { int64_t f1_split, p_split[BW_MAX_LEVELS], pooled[BW_MAX_LEVELS], gp[BW_MAX_LEVELS], total; };
+struct BwWorkspace {
+    int64_t f1_split, p_split[BW_MAX_LEVELS], pooled[BW_MAX_LEVELS], gp[BW_MAX_LEVELS], total;
+    int64_t mask1, cnt1, mask2, cnt2;            // sparse mode work lists
+    int units1, units2, words1, words2, unit_off2[BW_MAX_LEVELS + 1];
+};
 
 static BwWorkspace bw_workspace(int B, int C, int H, int W, int levels) {
     BwWorkspace w{};
@@ -588,6 +698,20 @@ static BwWorkspace bw_workspace(int B, int C, int H, int W, int levels) {
         w.p_split[l] = o; o = align(o + 2 * n);
         if (l > 0) { w.pooled[l] = o; o = align(o + n); w.gp[l] = o; o = align(o + n); }
         h /= 2; ww /= 2;
+    }
+    {   // sparse mode (CTA-pair kernel: 4 row blocks = 512 rows per unit)
+        const int N = H * W;
+        const OccLayout OL = make_occ_layout(H, W, levels);
+        w.units1 = ceil_div(ceil_div(N, BW_BM), 4);
+        int off = 0, hh = H, w2 = W;
+        for (int l = 0; l < levels; ++l) { w.unit_off2[l] = off; off += ceil_div(ceil_div(hh * w2, BW_BM), 4); hh /= 2; w2 /= 2; }
+        for (int l = levels; l <= BW_MAX_LEVELS; ++l) w.unit_off2[l] = off;
+        w.units2 = off;
+        w.words1 = OL.words; w.words2 = ceil_div(OL.qgroups, 32);
+        w.mask1 = o; o = align(o + (int64_t)B * w.units1 * w.words1 * 4);
+        w.cnt1 = o;  o = align(o + (int64_t)B * w.units1 * 4);
+        w.mask2 = o; o = align(o + (int64_t)B * w.units2 * w.words2 * 4);
+        w.cnt2 = o;  o = align(o + (int64_t)B * w.units2 * 4);
     }
     w.total = o;
     return w;
@@ -623,7 +747,8 @@ static unsigned long long* g_bw_trace = nullptr;
 void corr_pyramid_bwd_set_trace(void* p) { g_bw_trace = reinterpret_cast<unsigned long long*>(p); }
 
 int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2, float* gf1, float* gf2, void* ws,
-                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta) {
+                             int64_t ws_bytes, int B, int C, int H, int W, int levels, cudaStream_t s, int two_cta,
+                             const unsigned* occ) {
     if (C % 32 != 0) two_cta = 0;                       // each CTA of a pair streams C/2 channel rows
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) return PCFA_E_NODEVICE;
@@ -642,7 +767,20 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
     const int terms = (two_cta && env_terms == 1) ? 1 : 2;
     const float alpha = (1.0f / sqrtf((float)C)) * ((terms == 1 && env_debias) ? (1.0f + 3.5e-4f) : 1.0f);
 
+    const int stage2 = 2 * BW_A_BYTES + terms * (C / 2) * 128;
+    const int smem_fixed = 1024 + 256 + 2 * BW2_STG_BYTES;
+    int stages2 = (227 * 1024 - smem_fixed) / stage2;
+    if (stages2 > BW2_MAX_STAGES) stages2 = BW2_MAX_STAGES;
+    // Sparse mode needs the prefix sums of the units' live-chunk counts in shared memory; it is used when they fit without
+    // costing a ring stage (B * 20 units at 55x128: up to B = 22 with C = 256).
+    static const int env_sparse = [] { const char* e = getenv("PCFA_BWD_SPARSE"); return e ? atoi(e) : 1; }();
+    const int max_units = B * (wl.units1 > wl.units2 ? wl.units1 : wl.units2);
+    const int pre_bytes = 4 * (max_units + 2);
+    const bool sparse = occ && two_cta && env_sparse && levels <= BW_MAX_LEVELS &&
+                        (227 * 1024 - smem_fixed - pre_bytes) / stage2 >= stages2;
+
     // ---- one launch: operand prep (alpha folded in, pooling, TF32 hi/lo split) + zero-fill of the RED.ADD targets
+    // (+ in sparse mode the per-unit live masks of both passes)
     {
         BwPrepArgs pa{};
         pa.levels = levels; pa.B = B; pa.C = C; pa.alpha = alpha; pa.write_lo = terms == 2;
@@ -663,14 +801,22 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         const uintptr_t al = reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(gf1) |
                              reinterpret_cast<uintptr_t>(gf2) | reinterpret_cast<uintptr_t>(pa.f1_hi);
         const int vec = ((al & 15) == 0 && n % 4 == 0 && pa.f1_plane % 4 == 0) ? 1 : 0;
-        bw_prep_kernel<<<(unsigned)(flat_blocks + pooled_blocks), 256, 0, s>>>(f1, f2, pa, (int)flat_blocks, vec, nx, ny);
+        long long mask_blocks = 0;
+        if (sparse) {
+            pa.occ = occ; pa.OL = make_occ_layout(H, W, levels);
+            pa.mask1 = reinterpret_cast<unsigned*>(wsb + wl.mask1); pa.cnt1 = reinterpret_cast<int*>(wsb + wl.cnt1);
+            pa.mask2 = reinterpret_cast<unsigned*>(wsb + wl.mask2); pa.cnt2 = reinterpret_cast<int*>(wsb + wl.cnt2);
+            pa.units1 = wl.units1; pa.units2 = wl.units2; pa.words1 = wl.words1; pa.words2 = wl.words2;
+            for (int l = 0; l <= BW_MAX_LEVELS; ++l) pa.unit_off2[l] = wl.unit_off2[l];
+            mask_blocks = (long long)B * (wl.units1 + wl.units2);
+        }
+        if (flat_blocks + pooled_blocks + mask_blocks > 0x7fffffffLL) return PCFA_E_TOOLARGE;
+        bw_prep_kernel<<<(unsigned)(flat_blocks + pooled_blocks + mask_blocks), 256, 0, s>>>(f1, f2, pa, (int)flat_blocks, vec, nx, ny,
+                                                                                           (int)(flat_blocks + pooled_blocks));
         PCFA_TRY(after_launch());
     }
 
-    const int stage2 = 2 * BW_A_BYTES + terms * (C / 2) * 128;
-    int stages2 = (227 * 1024 - 1024 - 256 - 2 * BW2_STG_BYTES) / stage2;
-    if (stages2 > BW2_MAX_STAGES) stages2 = BW2_MAX_STAGES;
-    const int smem = two_cta ? stages2 * stage2 + 2 * BW2_STG_BYTES + 1024 + 256
+    const int smem = two_cta ? stages2 * stage2 + smem_fixed + (sparse ? pre_bytes : 0)
                              : BW_STAGES * (2 * BW_A_BYTES + 2 * C * 128) + 1024 + 256;
     static int smem_set = 0, smem2_set = 0;
     if (!two_cta && smem > smem_set) {
@@ -732,6 +878,10 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         P.units_per_sample = ceil_div(ceil_div(N, BW_BM), group);
         P.work_total = (long long)B * P.units_per_sample * P.chunks_total;
         P.out[0] = gf1;
+        if (sparse) {
+            P.sparse = 1; P.det = env_det; P.nunits = B * wl.units1; P.mask_words = wl.words1;
+            P.wl_mask = reinterpret_cast<const unsigned*>(wsb + wl.mask1); P.wl_cnt = reinterpret_cast<const int*>(wsb + wl.cnt1);
+        }
         if (two_cta) PCFA_TRY(enc3(enc, &maps.o[0], gf1, N, C, B, BW_BM, 16, CU_TENSOR_MAP_SWIZZLE_NONE));
         for (int l = 1; l < BW_MAX_LEVELS; ++l) maps.o[l] = maps.o[0];
         PCFA_TRY(launch(maps, P));
@@ -756,6 +906,10 @@ int corr_pyramid_backward_tc(const float* gpyr, const float* f1, const float* f2
         P.chunks_total = ceil_div(N, BW_BK);
         P.units_per_sample = off;
         P.work_total = (long long)B * off * P.chunks_total;
+        if (sparse) {
+            P.sparse = 1; P.det = env_det; P.nunits = B * wl.units2; P.mask_words = wl.words2;
+            P.wl_mask = reinterpret_cast<const unsigned*>(wsb + wl.mask2); P.wl_cnt = reinterpret_cast<const int*>(wsb + wl.cnt2);
+        }
         PCFA_TRY(launch(maps, P));
     }
     if (levels > 1) {

@@ -515,3 +515,121 @@ extern "C" int pcfa_corr_lookup_backward_cl(const float* grad_out, const float* 
                                             int W, int num_levels, int radius, pcfa_stream_t stream) {
     return lookup_backward(grad_out, coords, grad_pyramid, B, H, W, num_levels, radius, 1, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Occupancy bitmap of the gradient pyramid for the sparse build backward (common.cuh: OccLayout; pcfa_b200.h).
+// ONE launch for all lookups of a backward pass: a warp owns (32 consecutive queries = one bitmap row, one level) and
+// walks every lookup's footprint [floor(x/2^l) - r, +2r+2) x [floor(y/2^l) - r, +2r+2) — exactly the cells the
+// lookup-backward kernels above may write — setting the bits of the 32-cell chunks each clipped footprint row touches
+// in a shared-memory copy of its part of the row, which is then OR-ed into the global bitmap (<= a few words per warp).
+namespace pcfa {
+constexpr int OCC_MAX_LOOKUPS = 32;
+struct OccCoords { const float* p[OCC_MAX_LOOKUPS]; int n; };
+
+// grid (ceil(qgroups*levels/8), B, splits): slice z handles lookups z, z+splits, ...  Lanes are consecutive queries, whose
+// footprints mostly fall into the same chunks: a lane first collects its footprint's chunks in a 64-bit register mask, the
+// warp then OR-reduces the lanes' masks (REDUX) and four lanes write the result — per-lane, per-row shared-memory atomics on
+// the same few words serialise on the SM's shared-memory pipe (12-18 us for the whole launch).
+__global__ void __launch_bounds__(256)
+occ_mark_kernel(const OccCoords cl, unsigned* __restrict__ occ, const PyramidLayout L, const OccLayout OL, int N, int radius) {
+    extern __shared__ unsigned occ_rows[];                      // [8 warps][OL.words]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+    const int gw = blockIdx.x * 8 + warp;
+    const int qg = gw / L.levels, l = gw - qg * L.levels;
+    if (qg >= OL.qgroups) return;
+    unsigned* row = occ_rows + warp * OL.words;
+    const int w_lo = OL.chunk_off[l] >> 5, w_hi = (OL.chunk_off[l + 1] + 31) >> 5;      // words holding this level's columns
+    for (int w = w_lo + lane; w < w_hi; w += 32) row[w] = 0u;
+    __syncwarp();
+    const int q = min(qg * 32 + lane, N - 1);                   // tail lanes repeat the last query (same bitmap row)
+    const int Hl = L.h[l], Wl = L.w[l], F = 2 * radius + 2, colbase = OL.chunk_off[l];
+    const float scale = __int_as_float((127 - l) << 23);
+    const float* base = nullptr;
+    constexpr int U = 4;                                        // lookups whose coordinates are in flight together
+    for (int i0 = blockIdx.z; i0 < cl.n; i0 += U * gridDim.z) {
+        float sx[U], sy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * gridDim.z;
+            base = cl.p[i < cl.n ? i : i0] + (int64_t)b * 2 * N;
+            sx[u] = __ldg(base + q) * scale; sy[u] = __ldg(base + N + q) * scale;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * (int)gridDim.z >= cl.n) break;         // warp-uniform
+            const int ix0 = (int)fminf(fmaxf(floorf(sx[u]), -1.0e6f), 1.0e6f) - radius;   // same clamp as lookup_geom / lk_geom
+            const int iy0 = (int)fminf(fmaxf(floorf(sy[u]), -1.0e6f), 1.0e6f) - radius;
+            const int xlo = max(ix0, 0), xhi = min(ix0 + F, Wl) - 1;
+            const int ylo = max(iy0, 0), yhi = min(iy0 + F, Hl);
+            // this query's chunks as a 64-bit mask relative to its first chunk (a footprint spans (F-1)*Wl/32 + 2 chunks)
+            const bool act = xhi >= xlo && yhi > ylo;
+            const int cfirst = colbase + ((ylo * Wl + xlo) >> 5);
+            unsigned long long mask = 0ull;
+            if (act) {
+                for (int y = ylo; y < yhi; ++y) {
+                    const int d0 = colbase + ((y * Wl + xlo) >> 5) - cfirst, d1 = colbase + ((y * Wl + xhi) >> 5) - cfirst;
+                    if (d1 < 64) mask |= (1ull << d0) | (1ull << d1);
+                    else { atomicOr(row + ((cfirst + d0) >> 5), 1u << ((cfirst + d0) & 31)); atomicOr(row + ((cfirst + d1) >> 5), 1u << ((cfirst + d1) & 31)); }
+                }
+            }
+            // merge the 32 queries: masks whose first chunk lies within 64 chunks of the warp's (word-aligned) minimum are
+            // OR-reduced into four words (REDUX) and written by four lanes; scattered ones (noisy flow) go in directly
+            const int cmin = __reduce_min_sync(0xffffffffu, act ? cfirst : 0x7fffffff);
+            if (cmin == 0x7fffffff) continue;                                               // warp-uniform
+            const int cbase = cmin & ~31, off = cfirst - cbase;
+            const bool near = act && off < 64;
+            unsigned v[4] = {0u, 0u, 0u, 0u};
+            if (near) {
+                const unsigned long long lo = mask << (off & 63), hi = (off & 63) ? (mask >> (64 - (off & 63))) : 0ull;
+                v[0] = (unsigned)lo; v[1] = (unsigned)(lo >> 32); v[2] = (unsigned)hi; v[3] = (unsigned)(hi >> 32);
+            }
+            unsigned mine = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const unsigned t = __reduce_or_sync(0xffffffffu, v[k]); if (lane == k) mine = t; }
+            if (lane < 4 && mine) atomicOr(row + (cbase >> 5) + lane, mine);
+            if (act && !near && mask) {
+                const int w = cfirst >> 5, sh = cfirst & 31;
+                const unsigned long long lo = mask << sh;
+                atomicOr(row + w, (unsigned)lo);
+                if ((unsigned)(lo >> 32)) atomicOr(row + w + 1, (unsigned)(lo >> 32));
+                if (sh && (unsigned)(mask >> (64 - sh))) atomicOr(row + w + 2, (unsigned)(mask >> (64 - sh)));
+            }
+        }
+    }
+    __syncwarp();
+    unsigned* orow = occ + ((int64_t)b * OL.qgroups + qg) * OL.words;
+    for (int w = w_lo + lane; w < w_hi; w += 32) {
+        const unsigned v = row[w];
+        if (v) atomicOr(orow + w, v);
+    }
+}
+}  // namespace pcfa
+
+extern "C" int64_t pcfa_corr_occupancy_bytes(int B, int H, int W, int num_levels) {
+    if (B <= 0 || H <= 0 || W <= 0 || num_levels <= 0 || num_levels > 8) return 0;
+    const OccLayout OL = make_occ_layout(H, W, num_levels);
+    return (int64_t)B * OL.qgroups * OL.words * 4;
+}
+
+extern "C" int pcfa_corr_occupancy_mark(const float* const* coords_list, int n_lookups, uint32_t* occupancy, int B, int H, int W,
+                                        int num_levels, int radius, pcfa_stream_t stream) {
+    if (!coords_list || n_lookups < 0 || !occupancy || (reinterpret_cast<uintptr_t>(occupancy) & 3) || B <= 0 || B > 65535 ||
+        H <= 0 || W <= 0 || num_levels <= 0 || num_levels > 8 || radius < 0 || radius > 15)
+        return PCFA_E_BADARG;
+    const PyramidLayout L = make_pyramid_layout(B, H, W, num_levels);
+    const OccLayout OL = make_occ_layout(H, W, num_levels);
+    const size_t smem = (size_t)8 * OL.words * sizeof(unsigned);
+    if (smem > 48 * 1024) return PCFA_E_TOOLARGE;
+    for (int i0 = 0; i0 < n_lookups; i0 += OCC_MAX_LOOKUPS) {
+        OccCoords cl{};
+        cl.n = n_lookups - i0 < OCC_MAX_LOOKUPS ? n_lookups - i0 : OCC_MAX_LOOKUPS;
+        for (int i = 0; i < cl.n; ++i) {
+            if (!coords_list[i0 + i]) return PCFA_E_BADARG;
+            cl.p[i] = coords_list[i0 + i];
+        }
+        dim3 grid(ceil_div(OL.qgroups * num_levels, 8), B, cl.n >= 9 ? 4 : cl.n >= 3 ? 2 : 1);
+        occ_mark_kernel<<<grid, 256, smem, as_stream(stream)>>>(cl, reinterpret_cast<unsigned*>(occupancy), L, OL, H * W, radius);
+        PCFA_TRY(after_launch());
+    }
+    return PCFA_OK;
+}

@@ -17,6 +17,8 @@ def algorithmic_bytes(name: str, *, B: int, C: int, H: int, W: int, levels: int 
         pyr += B * N * h * w
         h, w = h // 2, w // 2
     D, F = 2 * radius + 1, 2 * radius + 2
+    if name.endswith("_occ"):                             # sparse-backward variants: same per-unit figure (SURVEY.md §8d counts the
+        name = name[:-4]                                  # dense gradient pyramid; skipped blocks are bytes NOT moved)
     if name == "pcfa_corr_pyramid_forward":
         return 4 * (2 * B * C * N + pyr)
     if name == "pcfa_corr_pyramid_backward":
