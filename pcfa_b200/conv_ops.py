@@ -14,6 +14,7 @@ from . import _lib
 
 _CL = torch.channels_last
 _DUMMY = {}
+_CUDNN_FUSED = os.environ.get("PCFA_CONV_FUSED", "1") != "0"   # 0: convolution + pcfa_bias_act_forward instead of cuDNN's fused epilogue
 _ENABLED = os.environ.get("PCFA_CONV_ACT", "1") != "0"       # 0: stock convolution + bias + ReLU modules (A/B measurements)
 
 
@@ -34,23 +35,29 @@ class _ConvBiasAct(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0, tail=None, transposed=None):
         lib = _lib.load()
-        if transposed is not None:                   # ConvTranspose2d: `transposed` = its output_padding
-            y = F.conv_transpose2d(x, weight, None, stride, padding, transposed, groups, dilation)
+        if _CUDNN_FUSED and transposed is None and relu and slope == 0.0:
+            # cuDNN's own convolution + bias + ReLU epilogue (one library call; 0.25 ms of the RAFT closure against the
+            # convolution followed by the in-place epilogue kernel below)
+            y = torch.ops.aten.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
+            cl = _is_cl(y)
         else:
-            y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
-        cl = _is_cl(y)
-        if not (cl or y.is_contiguous()):
-            y = y.contiguous()
-        C = y.shape[1]
-        inner = 1 if cl else y.shape[2] * y.shape[3]
-        st = lib.pcfa_bias_act_forward(_lib.ptr(y), _lib.ptr(bias), y.numel(), C, inner, int(relu), float(slope), 0 if y.dtype == torch.float32 else 1,
-                                       _lib.stream())
-        if st == -1:                                 # PCFA_E_BADARG: shape the vector kernels do not take (e.g. 2 output channels)
-            y.add_(bias.view(1, -1, 1, 1))
-            if relu:
-                y = F.leaky_relu_(y, slope) if slope else y.relu_()
-        else:
-            _lib.check(st, "pcfa_bias_act_forward")
+            if transposed is not None:               # ConvTranspose2d: `transposed` = its output_padding
+                y = F.conv_transpose2d(x, weight, None, stride, padding, transposed, groups, dilation)
+            else:
+                y = F.conv2d(x, weight, None, stride, padding, dilation, groups)
+            cl = _is_cl(y)
+            if not (cl or y.is_contiguous()):
+                y = y.contiguous()
+            C = y.shape[1]
+            inner = 1 if cl else y.shape[2] * y.shape[3]
+            st = lib.pcfa_bias_act_forward(_lib.ptr(y), _lib.ptr(bias), y.numel(), C, inner, int(relu), float(slope),
+                                           0 if y.dtype == torch.float32 else 1, _lib.stream())
+            if st == -1:                             # PCFA_E_BADARG: shape the vector kernels do not take (e.g. 2 output channels)
+                y.add_(bias.view(1, -1, 1, 1))
+                if relu:
+                    y = F.leaky_relu_(y, slope) if slope else y.relu_()
+            else:
+                _lib.check(st, "pcfa_bias_act_forward")
         if tail is not None:                         # overwrite the last channels (zero filters there): a cat without the copy
             y[:, y.shape[1] - tail.shape[1]:] = tail
         ctx.save_for_backward(weight, y if relu else None)
