@@ -417,6 +417,19 @@ int pcfa_softmax_rows_f16_backward(const void* attn, const void* grad_attn, void
 int pcfa_bias_act_forward(void* x, const void* bias, int64_t n, int C, int64_t inner, int relu, float slope, int dtype,
                           pcfa_stream_t stream);
 int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int64_t n, float slope, int dtype, pcfa_stream_t stream);
+/* grad_y given as rows `ld` elements apart (a channel slice of a wider channels-last tensor, i.e. the gradient of a
+ * concatenation): saves the .contiguous() copy.  y, grad_x: dense [rows][C]; C % 4 (8) == 0, ld % 4 (8) == 0. */
+int pcfa_relu_mask_backward_rows(const void* y, const void* grad_y, void* grad_x, int64_t rows, int C, int64_t ld, float slope,
+                                 int dtype, pcfa_stream_t stream);
+/* out = relu(a + b), element-wise, any dense layout shared by the three tensors: the tail of the encoders' residual blocks
+ * (models/raft/extractor.py:55,112) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */
+int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, int dtype, pcfa_stream_t stream);
+/* Coordinate bookkeeping of one RAFT/GMA refinement iteration in one launch (models/raft/raft.py:123-139):
+ * new_coords1 = coords1 + delta[..., 0:2], flow_cl = new_coords1 - coords0.  coords*: [B,2,H,W]; delta: channels-last with
+ * delta_ld (even) channels per pixel; flow_cl: [B,H,W,2] = torch.channels_last memory of [B,2,H,W]. */
+int pcfa_flow_step(const float* coords1, const float* coords0, const float* delta, int delta_ld, float* new_coords1,
+                   float* flow_cl, int B, int H, int W, pcfa_stream_t stream);
+
 
 /* --------------------------------------------------------------------------- on-device L-BFGS
  * The vector algebra of torch.optim.LBFGS.step (torch/optim/lbfgs.py; the reference's optimiser, attack_PCFA.py:97,114)

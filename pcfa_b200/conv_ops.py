@@ -31,6 +31,82 @@ def _dummy_like(shape, dtype, device, cl):
     return d
 
 
+def _channel_slice_ld(g: torch.Tensor, y: torch.Tensor) -> int:
+    """Pixel stride of g if g is a channel slice [:, a:b] of a wider channels-last tensor and y is dense channels-last of
+    the same shape and dtype (0 otherwise)."""
+    if g.dim() != 4 or g.dtype != y.dtype or g.shape != y.shape or not _is_cl(y) or g.is_contiguous(memory_format=_CL):
+        return 0
+    n, c, h, w = g.shape
+    sn, sc, sh, sw = g.stride()
+    if sc == 1 and sw > c and sh == w * sw and (n == 1 or sn == h * sh):
+        return sw
+    return 0
+
+
+class _AddReLU(Function):
+    """relu(a + b) as one launch (the tail of the encoders' residual blocks); the backward hands ONE masked gradient to both."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        out = torch.empty_like(a)
+        _lib.check(lib.pcfa_add_relu_forward(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.numel(), 0 if a.dtype == torch.float32 else 1,
+                                             _lib.stream()), "pcfa_add_relu_forward")
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (out,) = ctx.saved_tensors
+        g = g.contiguous(memory_format=_CL) if _is_cl(out) else g.contiguous()
+        gx = torch.empty_like(out)
+        _lib.check(lib.pcfa_relu_mask_backward(_lib.ptr(out), _lib.ptr(g), _lib.ptr(gx), out.numel(), 0.0, 0 if out.dtype == torch.float32 else 1,
+                                               _lib.stream()), "pcfa_relu_mask_backward")
+        return gx, gx
+
+
+def add_relu(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """relu(a + b); one kernel when both are CUDA tensors of the same dense layout (fp32 / fp16), torch ops otherwise."""
+    if (_ENABLED and a.is_cuda and a.shape == b.shape and a.dtype == b.dtype and a.dtype in (torch.float32, torch.float16)
+            and a.stride() == b.stride() and (a.is_contiguous() or _is_cl(a)) and a.numel() % 8 == 0
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        return _AddReLU.apply(a, b)
+    return torch.relu(a + b)
+
+
+class _FlowStep(Function):
+    """coords1 + delta_flow and the next iteration's channels-last flow in one launch (csrc/bias_act.cu: flow_step_kernel)."""
+
+    @staticmethod
+    def forward(ctx, coords1, coords0, delta):
+        lib = _lib.load()
+        B, _, H, W = coords1.shape
+        new = torch.empty_like(coords1)
+        flow = torch.empty((B, 2, H, W), device=coords1.device, dtype=torch.float32, memory_format=_CL)
+        _lib.check(lib.pcfa_flow_step(_lib.ptr(coords1), _lib.ptr(coords0), _lib.ptr(delta), delta.stride(3), _lib.ptr(new), _lib.ptr(flow),
+                                      B, H, W, _lib.stream()), "pcfa_flow_step")
+        ctx.mark_non_differentiable(flow)
+        return new, flow
+
+    @staticmethod
+    def backward(ctx, gnew, gflow):
+        return None, None, gnew                      # d new_coords1 / d delta = identity (coords1 is detached by the caller)
+
+
+def flow_step(coords1: torch.Tensor, coords0: torch.Tensor, delta: torch.Tensor):
+    """(coords1 + delta, channels-last (coords1 + delta - coords0)).  delta: [B,2,H,W] view of a channels-last tensor
+    (possibly a channel slice of the flow head's padded output)."""
+    ok = (coords1.is_cuda and coords1.dtype == torch.float32 and delta.dtype == torch.float32 and coords1.is_contiguous()
+          and coords0.is_contiguous() and delta.dim() == 4 and delta.shape == coords1.shape and delta.stride(1) == 1
+          and delta.stride(3) % 2 == 0 and delta.stride(2) == delta.shape[3] * delta.stride(3)
+          and (delta.shape[0] == 1 or delta.stride(0) == delta.shape[2] * delta.stride(2)) and delta.data_ptr() % 8 == 0)
+    if not (ok and _ENABLED):
+        new = coords1 + delta.contiguous()
+        return new, (new - coords0).detach().contiguous(memory_format=_CL)
+    return _FlowStep.apply(coords1, coords0, delta)
+
+
 class _ConvBiasAct(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation, groups, relu, slope=0.0, tail=None, transposed=None):
@@ -70,12 +146,19 @@ class _ConvBiasAct(Function):
         weight, y = ctx.saved_tensors
         shape, dtype, device, cl, stride, padding, dilation, groups, relu, slope, transposed = ctx.meta
         if relu:
-            g = g.contiguous(memory_format=_CL) if _is_cl(y) else g.contiguous()
-            if g.dtype != y.dtype:
-                g = g.to(y.dtype)
+            ld = _channel_slice_ld(g, y)
             gx = torch.empty_like(y)
-            st = lib.pcfa_relu_mask_backward(_lib.ptr(y), _lib.ptr(g), _lib.ptr(gx), y.numel(), slope, 0 if y.dtype == torch.float32 else 1,
-                                             _lib.stream())
+            if ld:                                   # g is a channel slice of a wider NHWC tensor (gradient of a concatenation)
+                st = lib.pcfa_relu_mask_backward_rows(_lib.ptr(y), _lib.ptr(g), _lib.ptr(gx), y.numel() // y.shape[1], y.shape[1], ld,
+                                                      slope, 0 if y.dtype == torch.float32 else 1, _lib.stream())
+            else:
+                st = -1
+            if st == -1:
+                g = g.contiguous(memory_format=_CL) if _is_cl(y) else g.contiguous()
+                if g.dtype != y.dtype:
+                    g = g.to(y.dtype)
+                st = lib.pcfa_relu_mask_backward(_lib.ptr(y), _lib.ptr(g), _lib.ptr(gx), y.numel(), slope, 0 if y.dtype == torch.float32 else 1,
+                                                 _lib.stream())
             if st == -1:
                 gx = torch.where(y > 0, g, g * slope)
             else:

@@ -73,6 +73,73 @@ relu_mask_f16_kernel(const __half* __restrict__ y, const __half* __restrict__ gy
     }
 }
 
+// grad_y is a channel slice of a wider channels-last tensor (the gradient of a concatenation): rows of C elements, ld apart
+__global__ void __launch_bounds__(BA_THREADS)
+relu_mask_rows_f32_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, int64_t n4, int c4, int64_t ld,
+                          float slope) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
+        const int64_t r = v / c4;
+        const int c = (int)(v - r * c4);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(y) + v), g = __ldg(reinterpret_cast<const float4*>(gy + r * ld) + c);
+        reinterpret_cast<float4*>(gx)[v] = make_float4(a.x > 0.f ? g.x : slope * g.x, a.y > 0.f ? g.y : slope * g.y, a.z > 0.f ? g.z : slope * g.z, a.w > 0.f ? g.w : slope * g.w);
+    }
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+relu_mask_rows_f16_kernel(const __half* __restrict__ y, const __half* __restrict__ gy, __half* __restrict__ gx, int64_t n8, int c8, int64_t ld,
+                          float slope) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n8; v += (int64_t)gridDim.x * BA_THREADS) {
+        const int64_t r = v / c8;
+        const int c = (int)(v - r * c8);
+        const uint4 ar = __ldg(reinterpret_cast<const uint4*>(y) + v);
+        uint4 gr = __ldg(reinterpret_cast<const uint4*>(gy + r * ld) + c);
+        const __half* a = reinterpret_cast<const __half*>(&ar);
+        __half* g = reinterpret_cast<__half*>(&gr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(__half2float(a[k]) > 0.f)) g[k] = __float2half_rn(slope * __half2float(g[k]));
+        reinterpret_cast<uint4*>(gx)[v] = gr;
+    }
+}
+
+// out = relu(a + b): the tail of a residual block (models/raft/extractor.py:55) in one pass instead of add + clamp
+__global__ void __launch_bounds__(BA_THREADS)
+add_relu_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n4) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a) + v), y = __ldg(reinterpret_cast<const float4*>(b) + v);
+        reinterpret_cast<float4*>(out)[v] = make_float4(fmaxf(x.x + y.x, 0.f), fmaxf(x.y + y.y, 0.f), fmaxf(x.z + y.z, 0.f), fmaxf(x.w + y.w, 0.f));
+    }
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+add_relu_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out, int64_t n8) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n8; v += (int64_t)gridDim.x * BA_THREADS) {
+        const uint4 xr = __ldg(reinterpret_cast<const uint4*>(a) + v), yr = __ldg(reinterpret_cast<const uint4*>(b) + v);
+        const __half* x = reinterpret_cast<const __half*>(&xr);
+        const __half* y = reinterpret_cast<const __half*>(&yr);
+        uint4 o;
+        __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) oh[k] = __float2half_rn(fmaxf(__half2float(__hadd(x[k], y[k])), 0.f));   // fp16 add like ATen
+        reinterpret_cast<uint4*>(out)[v] = o;
+    }
+}
+
+// One launch for the coordinate bookkeeping of a RAFT/GMA iteration (models/raft/raft.py:123-139): coords1 += delta_flow,
+// flow = coords1 - coords0.  coords: [B,2,H,W]; delta: channels-last with `ld` channels per pixel (the flow head's padded
+// output), channels 0..1 used; flow_cl: [B,H,W,2] (channels-last of [B,2,H,W]) for the next iteration's motion encoder.
+__global__ void __launch_bounds__(256)
+flow_step_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0, const float* __restrict__ delta, int ld,
+                 float* __restrict__ new_coords1, float* __restrict__ flow_cl, int B, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N, p = i - b * N;
+    const float2 d = __ldg(reinterpret_cast<const float2*>(delta + (int64_t)i * ld));
+    const int64_t o = (int64_t)b * 2 * N + p;
+    const float x = coords1[o] + d.x, y = coords1[o + N] + d.y;
+    new_coords1[o] = x; new_coords1[o + N] = y;
+    reinterpret_cast<float2*>(flow_cl)[i] = make_float2(x - coords0[o], y - coords0[o + N]);
+}
+
 static int ba_grid(int64_t nvec) {
     int64_t b = (nvec + BA_THREADS - 1) / BA_THREADS;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -113,5 +180,38 @@ extern "C" int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* 
     const int64_t nv = n / vec;
     if (dtype == 0) relu_mask_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const float*)y, (const float*)grad_y, (float*)grad_x, nv, slope);
     else            relu_mask_f16_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const __half*)y, (const __half*)grad_y, (__half*)grad_x, nv, slope);
+    return after_launch();
+}
+
+// grad_y rows `ld` elements apart (a channel slice of a channels-last tensor); y and grad_x dense [rows][C]
+extern "C" int pcfa_relu_mask_backward_rows(const void* y, const void* grad_y, void* grad_x, int64_t rows, int C, int64_t ld, float slope,
+                                            int dtype, pcfa_stream_t stream) {
+    if (!y || !grad_y || !grad_x || rows <= 0 || C <= 0 || ld < C || dtype < 0 || dtype > 1 || !(slope >= 0.f && slope < 1.f)) return PCFA_E_BADARG;
+    const int vec = dtype == 0 ? 4 : 8;
+    if (C % vec || ld % vec || ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(grad_x)) & 15))
+        return PCFA_E_BADARG;
+    const int64_t nv = rows * (C / vec);
+    if (dtype == 0) relu_mask_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const float*)y, (const float*)grad_y, (float*)grad_x, nv, C / vec, ld, slope);
+    else            relu_mask_rows_f16_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const __half*)y, (const __half*)grad_y, (__half*)grad_x, nv, C / vec, ld, slope);
+    return after_launch();
+}
+
+extern "C" int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, int dtype, pcfa_stream_t stream) {
+    if (!a || !b || !out || n <= 0 || dtype < 0 || dtype > 1) return PCFA_E_BADARG;
+    const int vec = dtype == 0 ? 4 : 8;
+    if (n % vec || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)) return PCFA_E_BADARG;
+    const int64_t nv = n / vec;
+    if (dtype == 0) add_relu_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const float*)a, (const float*)b, (float*)out, nv);
+    else            add_relu_f16_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>((const __half*)a, (const __half*)b, (__half*)out, nv);
+    return after_launch();
+}
+
+extern "C" int pcfa_flow_step(const float* coords1, const float* coords0, const float* delta, int delta_ld, float* new_coords1,
+                              float* flow_cl, int B, int H, int W, pcfa_stream_t stream) {
+    if (!coords1 || !coords0 || !delta || !new_coords1 || !flow_cl || B <= 0 || H <= 0 || W <= 0 || delta_ld < 2 || (delta_ld & 1)) return PCFA_E_BADARG;
+    if ((int64_t)B * H * W > 0x7fffffffLL) return PCFA_E_TOOLARGE;
+    if ((reinterpret_cast<uintptr_t>(delta) | reinterpret_cast<uintptr_t>(flow_cl)) & 7) return PCFA_E_BADARG;
+    const int n = B * H * W;
+    flow_step_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords1, coords0, delta, delta_ld, new_coords1, flow_cl, B, H * W);
     return after_launch();
 }

@@ -108,7 +108,8 @@ class ResidualBlock(nn.Module):
         y = _conv_norm_act(self.conv2, self.norm2, y, True)
         if self.downsample is not None:
             x = _conv_norm_act(self.downsample[0], self.downsample[1], x, False)
-        return self.relu(x + y)
+        from ..conv_ops import add_relu                     # relu(x + y) in one launch on the GPU
+        return add_relu(x, y)
 
 
 class BottleneckBlock(nn.Module):
@@ -136,7 +137,8 @@ class BottleneckBlock(nn.Module):
         y = _conv_norm_act(self.conv3, self.norm3, y, True)
         if self.downsample is not None:
             x = _conv_norm_act(self.downsample[0], self.downsample[1], x, False)
-        return self.relu(x + y)
+        from ..conv_ops import add_relu                     # relu(x + y) in one launch on the GPU
+        return add_relu(x, y)
 
 
 def _init_encoder(mod: nn.Module):
@@ -497,20 +499,25 @@ class RAFT(nn.Module):
                 if torch.is_grad_enabled() and os.environ.get("PCFA_GRU_STEP", "1") != "0":
                     from ..gru_ops import hoist_sources
                     step_sources = hoist_sources(hoist)
+        flow_cl = None
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
-            flow = coords1 - coords0
             need_up = (not test_mode) or itr == iters - 1
             with torch.autocast(dev_type, enabled=amp):
                 if cl:
-                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow.contiguous(memory_format=torch.channels_last),
+                    if flow_cl is None:
+                        flow_cl = (coords1 - coords0).contiguous(memory_format=torch.channels_last)
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow_cl,
                                                                  want_mask=need_up, cl=True, hoist=hoist, raw_mask=True,
                                                                  step_sources=step_sources, last=itr == iters - 1)
-                    delta_flow = delta_flow.contiguous()
+                    # coords1 += delta_flow and the next iteration's channels-last flow in one launch
+                    from ..conv_ops import flow_step
+                    coords1, flow_cl = flow_step(coords1, coords0, delta_flow)
                 else:
+                    flow = coords1 - coords0
                     net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, want_mask=need_up)
-            coords1 = coords1 + delta_flow
+                    coords1 = coords1 + delta_flow
             if need_up:
                 if up_mask is None:
                     flow_up = upflow8(coords1 - coords0)

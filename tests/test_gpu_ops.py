@@ -584,3 +584,53 @@ def test_gru_step_x_matches_sepconvgru_composition(dtype):
     assert rel(out, ref) < tol, rel(out, ref)
     for name, got, want in (("h", a.grad, ra.grad), ("m1", b1.grad, rm1.grad), ("m2", b2.grad, rm2.grad), ("inp", i_.grad, ri.grad)):
         assert rel(got, want) < tol, (name, rel(got, want))
+
+
+# ----------------------------------------------------------------------------------- small fused glue ops (round 2)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("cl", [True, False])
+def test_add_relu_matches_torch(dtype, cl):
+    from pcfa_b200.conv_ops import add_relu
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 64, 22, 32, generator=g).cuda().to(dtype)
+    b = torch.randn(2, 64, 22, 32, generator=g).cuda().to(dtype)
+    if cl:
+        a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    a1, b1, a2, b2 = (t.clone().requires_grad_(True) for t in (a, b, a, b))
+    out, ref = add_relu(a1, b1), torch.relu(a2 + b2)
+    assert out.stride() == ref.stride() and torch.equal(out, ref)
+    go = torch.randn(out.shape, generator=g).cuda().to(dtype)
+    (out * go).sum().backward()
+    (ref * go).sum().backward()
+    assert torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+
+
+def test_relu_mask_backward_on_channel_slices_of_a_concatenation():
+    """conv_act's backward reads its gradient straight out of a wider channels-last tensor (the gradient of a cat)."""
+    from pcfa_b200.conv_ops import conv_act
+    g = torch.Generator().manual_seed(9)
+    convs = [torch.nn.Conv2d(16, c, 3, padding=1).cuda().to(memory_format=torch.channels_last) for c in (192, 64)]
+    for cv in convs:
+        for p in cv.parameters():
+            p.requires_grad = False
+    x = torch.randn(1, 16, 20, 24, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    w = torch.randn(1, 256, 20, 24, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    (torch.cat([conv_act(cv, xa, True) for cv in convs], 1) * w).sum().backward()
+    (torch.cat([torch.relu(cv(xb)) for cv in convs], 1) * w).sum().backward()
+    assert_close(npy(xa.grad), npy(xb.grad), what="grad through cat slices", **TOL)
+
+
+def test_flow_step_matches_torch_and_passes_the_gradient():
+    from pcfa_b200.conv_ops import flow_step
+    g = torch.Generator().manual_seed(2)
+    c1 = torch.randn(2, 2, 11, 16, generator=g).cuda()
+    c0 = torch.randn(2, 2, 11, 16, generator=g).cuda()
+    d8 = torch.randn(2, 8, 11, 16, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    new, flow = flow_step(c1, c0, d8[:, :2])
+    ref = c1 + d8.detach()[:, :2]
+    assert torch.equal(new, ref) and torch.equal(flow, ref - c0)
+    assert flow.is_contiguous(memory_format=torch.channels_last) and not flow.requires_grad
+    go = torch.randn(new.shape, generator=g).cuda()
+    (new * go).sum().backward()
+    assert torch.equal(d8.grad[:, :2], go) and float(d8.grad[:, 2:].abs().max()) == 0.0
