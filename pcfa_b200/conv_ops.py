@@ -79,32 +79,39 @@ class _FlowStep(Function):
     """coords1 + delta_flow and the next iteration's channels-last flow in one launch (csrc/bias_act.cu: flow_step_kernel)."""
 
     @staticmethod
-    def forward(ctx, coords1, coords0, delta):
+    def forward(ctx, coords1, coords0, delta, flow_channels):
         lib = _lib.load()
         B, _, H, W = coords1.shape
         new = torch.empty_like(coords1)
-        flow = torch.empty((B, 2, H, W), device=coords1.device, dtype=torch.float32, memory_format=_CL)
+        flow = torch.empty((B, flow_channels, H, W), device=coords1.device, dtype=torch.float32, memory_format=_CL)
         _lib.check(lib.pcfa_flow_step(_lib.ptr(coords1), _lib.ptr(coords0), _lib.ptr(delta), delta.stride(3), _lib.ptr(new), _lib.ptr(flow),
-                                      B, H, W, _lib.stream()), "pcfa_flow_step")
+                                      flow_channels, B, H, W, _lib.stream()), "pcfa_flow_step")
         ctx.mark_non_differentiable(flow)
         return new, flow
 
     @staticmethod
     def backward(ctx, gnew, gflow):
-        return None, None, gnew                      # d new_coords1 / d delta = identity (coords1 is detached by the caller)
+        return None, None, gnew, None                # d new_coords1 / d delta = identity (coords1 is detached by the caller)
 
 
-def flow_step(coords1: torch.Tensor, coords0: torch.Tensor, delta: torch.Tensor):
-    """(coords1 + delta, channels-last (coords1 + delta - coords0)).  delta: [B,2,H,W] view of a channels-last tensor
-    (possibly a channel slice of the flow head's padded output)."""
+def padded_flow(flow: torch.Tensor, channels: int) -> torch.Tensor:
+    """[B, channels, H, W] channels-last with the flow in channels 0..1 and zeros behind (flow_step's output format)."""
+    out = torch.zeros((flow.shape[0], channels, flow.shape[2], flow.shape[3]), device=flow.device, dtype=flow.dtype).contiguous(memory_format=_CL)
+    out[:, :flow.shape[1]] = flow
+    return out
+
+
+def flow_step(coords1: torch.Tensor, coords0: torch.Tensor, delta: torch.Tensor, flow_channels: int = 2):
+    """(coords1 + delta, channels-last (coords1 + delta - coords0) zero-padded to flow_channels).  delta: [B,2,H,W] view of
+    a channels-last tensor (possibly a channel slice of the flow head's padded output)."""
     ok = (coords1.is_cuda and coords1.dtype == torch.float32 and delta.dtype == torch.float32 and coords1.is_contiguous()
           and coords0.is_contiguous() and delta.dim() == 4 and delta.shape == coords1.shape and delta.stride(1) == 1
           and delta.stride(3) % 2 == 0 and delta.stride(2) == delta.shape[3] * delta.stride(3)
           and (delta.shape[0] == 1 or delta.stride(0) == delta.shape[2] * delta.stride(2)) and delta.data_ptr() % 8 == 0)
     if not (ok and _ENABLED):
         new = coords1 + delta.contiguous()
-        return new, (new - coords0).detach().contiguous(memory_format=_CL)
-    return _FlowStep.apply(coords1, coords0, delta)
+        return new, padded_flow((new - coords0).detach(), flow_channels)
+    return _FlowStep.apply(coords1, coords0, delta, flow_channels)
 
 
 class _ConvBiasAct(Function):

@@ -129,7 +129,7 @@ add_relu_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, 
 // output), channels 0..1 used; flow_cl: [B,H,W,2] (channels-last of [B,2,H,W]) for the next iteration's motion encoder.
 __global__ void __launch_bounds__(256)
 flow_step_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0, const float* __restrict__ delta, int ld,
-                 float* __restrict__ new_coords1, float* __restrict__ flow_cl, int B, int N) {
+                 float* __restrict__ new_coords1, float* __restrict__ flow_cl, int fld, int B, int N) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= B * N) return;
     const int b = i / N, p = i - b * N;
@@ -137,7 +137,9 @@ flow_step_kernel(const float* __restrict__ coords1, const float* __restrict__ co
     const int64_t o = (int64_t)b * 2 * N + p;
     const float x = coords1[o] + d.x, y = coords1[o + N] + d.y;
     new_coords1[o] = x; new_coords1[o + N] = y;
-    reinterpret_cast<float2*>(flow_cl)[i] = make_float2(x - coords0[o], y - coords0[o + N]);
+    float2* f = reinterpret_cast<float2*>(flow_cl + (int64_t)i * fld);
+    f[0] = make_float2(x - coords0[o], y - coords0[o + N]);
+    for (int k = 1; k < fld / 2; ++k) f[k] = make_float2(0.f, 0.f);          // zero channels for a tensor-core convf1
 }
 
 static int ba_grid(int64_t nvec) {
@@ -207,11 +209,12 @@ extern "C" int pcfa_add_relu_forward(const void* a, const void* b, void* out, in
 }
 
 extern "C" int pcfa_flow_step(const float* coords1, const float* coords0, const float* delta, int delta_ld, float* new_coords1,
-                              float* flow_cl, int B, int H, int W, pcfa_stream_t stream) {
-    if (!coords1 || !coords0 || !delta || !new_coords1 || !flow_cl || B <= 0 || H <= 0 || W <= 0 || delta_ld < 2 || (delta_ld & 1)) return PCFA_E_BADARG;
+                              float* flow_cl, int flow_ld, int B, int H, int W, pcfa_stream_t stream) {
+    if (!coords1 || !coords0 || !delta || !new_coords1 || !flow_cl || B <= 0 || H <= 0 || W <= 0 || delta_ld < 2 || (delta_ld & 1) ||
+        flow_ld < 2 || (flow_ld & 1)) return PCFA_E_BADARG;
     if ((int64_t)B * H * W > 0x7fffffffLL) return PCFA_E_TOOLARGE;
     if ((reinterpret_cast<uintptr_t>(delta) | reinterpret_cast<uintptr_t>(flow_cl)) & 7) return PCFA_E_BADARG;
     const int n = B * H * W;
-    flow_step_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords1, coords0, delta, delta_ld, new_coords1, flow_cl, B, H * W);
+    flow_step_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords1, coords0, delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
     return after_launch();
 }

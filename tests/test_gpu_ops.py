@@ -630,6 +630,9 @@ def test_flow_step_matches_torch_and_passes_the_gradient():
     new, flow = flow_step(c1, c0, d8[:, :2])
     ref = c1 + d8.detach()[:, :2]
     assert torch.equal(new, ref) and torch.equal(flow, ref - c0)
+    new8, flow8 = flow_step(c1, c0, d8[:, :2], 8)                            # zero-padded flow for the tensor-core convf1
+    assert torch.equal(new8, ref) and flow8.shape == (2, 8, 11, 16) and flow8.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(flow8[:, :2], ref - c0) and float(flow8[:, 2:].abs().max()) == 0.0
     assert flow.is_contiguous(memory_format=torch.channels_last) and not flow.requires_grad
     go = torch.randn(new.shape, generator=g).cuda()
     (new * go).sum().backward()
