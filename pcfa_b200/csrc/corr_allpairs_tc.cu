@@ -29,11 +29,14 @@ namespace pcfa {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
 #ifndef PCFA_TC_PH
-#define PCFA_TC_PH 8
-#define PCFA_TC_PW 16
+#define PCFA_TC_PH 4
+#define PCFA_TC_PW 32
 #endif
-constexpr int TC_PH = PCFA_TC_PH, TC_PW = PCFA_TC_PW;          // target patch
+constexpr int TC_PH = PCFA_TC_PH, TC_PW = PCFA_TC_PW;          // target patch (4 x 32; -DPCFA_TC_PH=8 -DPCFA_TC_PW=16: round-1 shape)
+constexpr bool TC_WIDE = (TC_PH == 4 && TC_PW == 32);          // a TMEM lane quarter (one warp) = one 32-pixel patch row
 constexpr int TC_STAGES = 3;
+constexpr int TC2_SLOTS = 5;                // CTA-pair kernel: ring of single [128 x 64 bf16] target tiles (hi, mid, hi, ...)
+constexpr int TC2_XBUF_BYTES = 16 * 1024;   // CTA-pair kernel: 1 KB per epilogue warp for the level-1 pooling exchange
 constexpr int TC_THREADS = 384;             // 4 control warps + 8 epilogue warps
 constexpr int TC2_THREADS = 640;            // CTA-pair kernel: 4 control warps + 16 epilogue warps (lane quarter x column quarter)
 constexpr int TC_TILE_BYTES = 128 * 128;      // one [128 rows x 64 bf16] SW128 tile
@@ -257,9 +260,10 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_q = base;
     const uint32_t smem_a = base + 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES;
-    const uint32_t bars = smem_a + TC_STAGES * 2 * TC_TILE_BYTES;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC_STAGES;
-    const uint32_t bar_qfull = bars + 16 * TC_STAGES, bar_qempty = bar_qfull + 8;
+    const uint32_t xbuf = smem_a + TC2_SLOTS * TC_TILE_BYTES;
+    const uint32_t bars = xbuf + TC2_XBUF_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * TC2_SLOTS;
+    const uint32_t bar_qfull = bars + 16 * TC2_SLOTS, bar_qempty = bar_qfull + 8;
     const uint32_t bar_tfull = bar_qempty + 8, bar_tempty = bar_tfull + 16;
     const uint32_t tmem_slot = bar_tempty + 16;
 
@@ -270,7 +274,7 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
     const long long t_begin = P.total_pairs * cid / ncl, t_end = P.total_pairs * (cid + 1) / ncl;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < TC2_SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_qfull, 1); mbar_init(bar_qempty, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -307,13 +311,14 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             // an absent second tile of an odd tile count reads a fully out-of-range box: zero-filled
             const int y0 = c.valid ? c.ty * TC_PH : (P.lh[0] + TC_PH), x0 = c.tx * TC_PW;
             for (int kc = 0; kc < P.kchunks; ++kc) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * 2 * TC_TILE_BYTES);
-                const uint32_t dst = smem_a + stage * 2 * TC_TILE_BYTES;
-                const uint32_t lb = leader_bar(bar_full + 8 * stage);
-                tma2_load_4d(dst, &maps.t[c.level], lb, kc * TC_BK, x0, y0, c.b);
-                tma2_load_4d(dst + TC_TILE_BYTES, &maps.t[c.level], lb, kc * TC_BK, x0, y0, P.B + c.b);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {          // hi tile, then mid tile: one ring slot each
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * TC_TILE_BYTES);        // both CTAs' bytes
+                    tma2_load_4d(smem_a + stage * TC_TILE_BYTES, &maps.t[c.level], leader_bar(bar_full + 8 * stage), kc * TC_BK, x0, y0,
+                                 part * P.B + c.b);
+                    if (++stage == TC2_SLOTS) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -327,19 +332,30 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
             for (int kc = 0; kc < P.kchunks; ++kc) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                tc_fence_after();
-                const uint32_t a_hi = smem_a + stage * 2 * TC_TILE_BYTES, a_mid = a_hi + TC_TILE_BYTES;
                 const uint32_t b_hi = smem_q + kc * TC_TILE_BYTES, b_mid = smem_q + (TC_MAX_KCHUNKS + kc) * TC_TILE_BYTES;
+                {   // targets' hi tile: hi*hi + hi*mid
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_a + stage * TC_TILE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / 16; ++kk) {
-                    const uint32_t ko = kk * 32;
-                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, (kc | kk) != 0);
-                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16_2cta, 1);
-                    tc2_mma_bf16(d_tmem, umma_desc_sw128(a_mid + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, 1);
+                    for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdescBf16_2cta, (kc | kk) != 0);
+                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_mid + ko), kIdescBf16_2cta, 1);
+                    }
+                    tc2_commit_mc(bar_empty + 8 * stage);
+                    if (++stage == TC2_SLOTS) { stage = 0; phase ^= 1; }
                 }
-                tc2_commit_mc(bar_empty + 8 * stage);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                {   // targets' mid tile: mid*hi
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_mid = smem_a + stage * TC_TILE_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 16; ++kk)
+                        tc2_mma_bf16(d_tmem, umma_desc_sw128(a_mid + kk * 32), umma_desc_sw128(b_hi + kk * 32), kIdescBf16_2cta, 1);
+                    tc2_commit_mc(bar_empty + 8 * stage);
+                    if (++stage == TC2_SLOTS) { stage = 0; phase ^= 1; }
+                }
             }
             tc2_commit_mc(bar_tfull + 8 * acc);
             const bool last_of_block = (t + 1 == t_end) || ((t + 1) / P.pairs_per_qb2 != key);
@@ -371,10 +387,10 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
             float* out = pyr + P.lvl_off[c.level] + ((long long)c.b * P.N + q0) * qstride + (long long)y * Wl + x;
             const int nq = P.N - q0;                                // valid queries from q0 on (may be <= 0)
             const bool pool1 = P.fuse_l1 && c.valid && c.level == 0;        // warp-uniform
-            const int y1 = c.ty * (TC_PH / 2) + ew, x1 = c.tx * (TC_PW / 2) + (xl >> 1);
+            const int y1 = c.ty * (TC_PH / 2) + (TC_WIDE ? (ew >> 1) : ew), x1 = c.tx * (TC_PW / 2) + (xl >> 1);
             const bool ok1 = pool1 && y1 < P.lh[1] && x1 < P.lw[1];
             const long long q1stride = (long long)P.lh[1] * P.lw[1];
-            float* out1 = pyr + P.lvl_off[1] + ((long long)c.b * P.N + q0 + sub) * q1stride + (long long)y1 * P.lw[1] + x1;
+            float* out1 = pyr + P.lvl_off[1] + ((long long)c.b * P.N + q0 + (TC_WIDE ? 0 : sub)) * q1stride + (long long)y1 * P.lw[1] + x1;
             mbar_wait(bar_tfull + 8 * acc, accphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 256 + cq * 64;
@@ -398,7 +414,35 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
                     }
                 }
                 __syncwarp();
-                if (pool1) {
+                if (TC_WIDE && pool1) {
+                    // 4 x 32 patches: this warp holds ONE patch row, its partner (ew ^ 1, same CTA) the other row of the 2x2
+                    // blocks.  x pairs are reduced in the warp (the two lanes of a pair end up with the sums of two different
+                    // queries), then each warp keeps half of the 16 query pairs and hands the other half to its partner
+                    // through 1 KB of shared memory (two 64-thread named barriers per 32 columns).
+                    float xr[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float a0 = __uint_as_float(v[2 * k]), a1 = __uint_as_float(v[2 * k + 1]);
+                        xr[k] = (bx ? a1 : a0) + __shfl_xor_sync(0xffffffffu, bx ? a0 : a1, 1);     // query c0 + 2k + bx
+                    }
+                    const bool even = (ew & 1) == 0;
+                    const int bar_id = 1 + (warp - 4) / 2;                                          // 8 warp pairs: ids 1..8
+                    const uint32_t mine = xbuf + (uint32_t)(warp - 4) * 1024u + lane * 4u;
+                    const uint32_t theirs = xbuf + (uint32_t)((warp - 4) ^ 1) * 1024u + lane * 4u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine + i * 128u), "f"(even ? xr[8 + i] : xr[i]) : "memory");
+                    named_bar_sync(bar_id, 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float o;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(theirs + i * 128u) : "memory");
+                        const float r = 0.25f * ((even ? xr[i] : xr[8 + i]) + o);
+                        const int qrel = c0 + (even ? 0 : 16) + 2 * i + (bx ? 1 : 0);
+                        if (ok1 && qrel < nq) __stcs(out1 + (long long)qrel * q1stride, r);
+                    }
+                    named_bar_sync(bar_id, 64);                      // the partner has read this chunk: the buffer may be rewritten
+                } else if (pool1) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
@@ -640,7 +684,8 @@ int corr_pyramid_forward_tc(const float* fmap1, const float* fmap2, float* pyram
     P.tiles_per_qb = toff;
     P.total_tiles = (long long)B * P.qblocks * toff;
 
-    const int smem = 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES + TC_STAGES * 2 * TC_TILE_BYTES + 1024 + 256;
+    const int smem = two_cta ? 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES + TC2_SLOTS * TC_TILE_BYTES + TC2_XBUF_BYTES + 1024 + 256
+                             : 2 * TC_MAX_KCHUNKS * TC_TILE_BYTES + TC_STAGES * 2 * TC_TILE_BYTES + 1024 + 256;
     if (two_cta) {
         P.qb2blocks = ceil_div(P.qblocks, 2);
         P.pairs_per_qb2 = ceil_div(toff, 2);
