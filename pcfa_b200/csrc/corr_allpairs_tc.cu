@@ -11,13 +11,14 @@
 // products hi*hi + hi*mid + mid*hi are accumulated in fp32 in TMEM, giving ~1e-5 relative error per
 // product — inside the 1e-3 parity bar with two orders of margin, at 1.5x the tensor work of TF32.
 //
-// Tile mapping: UMMA M = 128 *targets* (an 8 x 16 patch of level l, fetched by one 4-D TMA box from
+// Tile mapping: UMMA M = 128 *targets* (a 4 x 32 pixel patch of level l, fetched by one 4-D TMA box from
 // the channel-last split copy of pool_l(fmap2), out-of-range rows/cols zero-filled), UMMA N = 128
-// *queries*.  TMEM lane == target, so an epilogue warp's 32 lanes are two 16-pixel row segments and
-// every global store instruction writes two full 64-byte runs of one query's row: coalesced without
-// staging through shared memory.  The 128-query operand (hi+mid, all channels: 128 KB) stays
-// resident in shared memory while the CTA sweeps target tiles; the target operand streams through a
-// 3-stage TMA/mbarrier ring.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
+// *queries*.  TMEM lane == target, so an epilogue warp's 32 lanes are one 32-pixel row segment and
+// every global store instruction writes one full 128-byte line of one query's row: coalesced without
+// staging through shared memory (round 1 used 8 x 16 patches = two 64-byte half lines per store, which
+// alone cost 63.5 instead of 44.6 us, profiles/fwd_store_pattern_r2.txt).  The 128-query operand (hi+mid, all
+// channels: 128 KB) stays resident in shared memory while the CTA sweeps target tiles; the target operand streams
+// through a TMA/mbarrier ring.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one thread),
 // 2 = TMEM allocator, 4..11 = epilogue (TMEM -> registers -> global), double-buffered accumulators.
 // The 1/sqrt(C) factor is folded into the query operand before the bf16 split.
 #include "tc_common.cuh"
@@ -366,8 +367,9 @@ corr_pyramid_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams P, f
     } else if (warp >= 4) {
         // ===================================================================== epilogue (16 warps, both CTAs)
         // warp = (TMEM lane quarter ew, query-column quarter cq).  Level 0 is stored straight from the accumulator
-        // (lane == target: every store instruction writes two 64-byte runs).  Level 1 = 2x2 floor pooling of level 0
-        // (F.avg_pool2d, corr.py:25-27) is derived here instead of spending level-1 GEMM tiles (-21 % tensor work):
+        // (lane == target: every store instruction writes one 128-byte line).  Level 1 = 2x2 floor pooling of level 0
+        // (F.avg_pool2d, corr.py:25-27) is derived here instead of spending level-1 GEMM tiles (-21 % tensor work).
+        // 4 x 32 patches (TC_WIDE): see the exchange below.  8 x 16 patches (round-1 shape, compile-time option):
         // a warp's 32 lanes are two 16-pixel patch rows, so the 2x2 blocks live on lane bits 0 (x) and 4 (y).  Four
         // columns (queries) are reduced together by a transpose-reduce — 3 shuffles per 4 columns — after which the
         // four lanes of a block hold the sums of four different queries: one store writes 4 queries x 8 cells.
