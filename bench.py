@@ -134,7 +134,11 @@ def measured_traffic(entry_point):
         return None
     try:
         ep = json.loads(files[-1].read_text())["entry_points"]
-        return ep.get(entry_point, ep.get(entry_point[:-3]) if entry_point.endswith("_cl") else None)
+        for name in (entry_point, entry_point[:-3] if entry_point.endswith("_cl") else None,
+                     entry_point[:-4] if entry_point.endswith("_occ") else None):
+            if name and name in ep:
+                return ep[name]
+        return None
     except Exception:
         return None
 

@@ -51,6 +51,8 @@ if len(sys.argv) > 3:
     g = lambda *names: sum(k.get(n, 0) for n in names)
     ep = {"pcfa_corr_pyramid_forward": g("prep_targets_kernel", "corr_pyramid_tc2_kernel"),
           "pcfa_corr_pyramid_backward": g("bw_prep_kernel", "bw_unpool_kernel") + 2 * k.get("corr_pyramid_bwd_tc2_kernel", 0),
+          "pcfa_corr_pyramid_backward_occ": g("bw_prep_kernel", "bw_unpool_kernel") + 2 * k.get("corr_pyramid_bwd_tc2_kernel", 0),
+          "pcfa_corr_occupancy_mark": k.get("occ_mark_kernel", 0),
           "pcfa_corr_lookup_forward": k.get("corr_lookup_fwd_cl2_kernel<4, 4>", k.get("corr_lookup_fwd_kernel<4>", 0)),
           "pcfa_corr_lookup_backward": k.get("corr_lookup_bwd_cl2_kernel<4, 4>", k.get("corr_lookup_bwd_kernel<4>", 0))}
     json.dump({"source": out_txt + " (dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the captured launches)",
