@@ -428,8 +428,8 @@ int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, in
  * new_coords1 = coords1 + delta[..., 0:2], flow_cl = new_coords1 - coords0.  coords*: [B,2,H,W]; delta: channels-last with
  * delta_ld (even) channels per pixel; flow_cl: [B,H,W,flow_ld] = torch.channels_last memory of [B,flow_ld,H,W], channels 2.. are
  * zero-filled (flow_ld = 8 lets the 7x7 convolution on the flow run as a tensor-core implicit GEMM). */
-int pcfa_flow_step(const float* coords1, const float* coords0, const float* delta, int delta_ld, float* new_coords1,
-                   float* flow_cl, int flow_ld, int B, int H, int W, pcfa_stream_t stream);
+int pcfa_flow_step(const float* coords1, const float* coords0, const void* delta, int delta_ld, int delta_dtype /* 0 fp32, 1 fp16 */,
+                   float* new_coords1, float* flow_cl, int flow_ld, int B, int H, int W, pcfa_stream_t stream);
 
 
 /* --------------------------------------------------------------------------- on-device L-BFGS

@@ -84,13 +84,17 @@ class _FlowStep(Function):
         B, _, H, W = coords1.shape
         new = torch.empty_like(coords1)
         flow = torch.empty((B, flow_channels, H, W), device=coords1.device, dtype=torch.float32, memory_format=_CL)
-        _lib.check(lib.pcfa_flow_step(_lib.ptr(coords1), _lib.ptr(coords0), _lib.ptr(delta), delta.stride(3), _lib.ptr(new), _lib.ptr(flow),
+        _lib.check(lib.pcfa_flow_step(_lib.ptr(coords1), _lib.ptr(coords0), _lib.ptr(delta), delta.stride(3),
+                                      0 if delta.dtype == torch.float32 else 1, _lib.ptr(new), _lib.ptr(flow),
                                       flow_channels, B, H, W, _lib.stream()), "pcfa_flow_step")
+        ctx.ddtype = delta.dtype
         ctx.mark_non_differentiable(flow)
         return new, flow
 
     @staticmethod
     def backward(ctx, gnew, gflow):
+        if gnew is not None and gnew.dtype != ctx.ddtype:
+            gnew = gnew.to(ctx.ddtype)
         return None, None, gnew, None                # d new_coords1 / d delta = identity (coords1 is detached by the caller)
 
 
@@ -104,12 +108,12 @@ def padded_flow(flow: torch.Tensor, channels: int) -> torch.Tensor:
 def flow_step(coords1: torch.Tensor, coords0: torch.Tensor, delta: torch.Tensor, flow_channels: int = 2):
     """(coords1 + delta, channels-last (coords1 + delta - coords0) zero-padded to flow_channels).  delta: [B,2,H,W] view of
     a channels-last tensor (possibly a channel slice of the flow head's padded output)."""
-    ok = (coords1.is_cuda and coords1.dtype == torch.float32 and delta.dtype == torch.float32 and coords1.is_contiguous()
+    ok = (coords1.is_cuda and coords1.dtype == torch.float32 and delta.dtype in (torch.float32, torch.float16) and coords1.is_contiguous()
           and coords0.is_contiguous() and delta.dim() == 4 and delta.shape == coords1.shape and delta.stride(1) == 1
           and delta.stride(3) % 2 == 0 and delta.stride(2) == delta.shape[3] * delta.stride(3)
           and (delta.shape[0] == 1 or delta.stride(0) == delta.shape[2] * delta.stride(2)) and delta.data_ptr() % 8 == 0)
     if not (ok and _ENABLED):
-        new = coords1 + delta.contiguous()
+        new = coords1 + delta.float().contiguous()
         return new, padded_flow((new - coords0).detach(), flow_channels)
     return _FlowStep.apply(coords1, coords0, delta, flow_channels)
 

@@ -127,13 +127,16 @@ add_relu_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, 
 // One launch for the coordinate bookkeeping of a RAFT/GMA iteration (models/raft/raft.py:123-139): coords1 += delta_flow,
 // flow = coords1 - coords0.  coords: [B,2,H,W]; delta: channels-last with `ld` channels per pixel (the flow head's padded
 // output), channels 0..1 used; flow_cl: [B,H,W,2] (channels-last of [B,2,H,W]) for the next iteration's motion encoder.
+template <typename TD>
 __global__ void __launch_bounds__(256)
-flow_step_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0, const float* __restrict__ delta, int ld,
+flow_step_kernel(const float* __restrict__ coords1, const float* __restrict__ coords0, const TD* __restrict__ delta, int ld,
                  float* __restrict__ new_coords1, float* __restrict__ flow_cl, int fld, int B, int N) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= B * N) return;
     const int b = i / N, p = i - b * N;
-    const float2 d = __ldg(reinterpret_cast<const float2*>(delta + (int64_t)i * ld));
+    float2 d;
+    if (sizeof(TD) == 4) d = __ldg(reinterpret_cast<const float2*>(delta + (int64_t)i * ld));
+    else d = __half22float2(*reinterpret_cast<const __half2*>(delta + (int64_t)i * ld));       // GMA: fp16 flow head
     const int64_t o = (int64_t)b * 2 * N + p;
     const float x = coords1[o] + d.x, y = coords1[o + N] + d.y;
     new_coords1[o] = x; new_coords1[o + N] = y;
@@ -208,13 +211,17 @@ extern "C" int pcfa_add_relu_forward(const void* a, const void* b, void* out, in
     return after_launch();
 }
 
-extern "C" int pcfa_flow_step(const float* coords1, const float* coords0, const float* delta, int delta_ld, float* new_coords1,
-                              float* flow_cl, int flow_ld, int B, int H, int W, pcfa_stream_t stream) {
+extern "C" int pcfa_flow_step(const float* coords1, const float* coords0, const void* delta, int delta_ld, int delta_dtype,
+                              float* new_coords1, float* flow_cl, int flow_ld, int B, int H, int W, pcfa_stream_t stream) {
+    if (delta_dtype < 0 || delta_dtype > 1) return PCFA_E_BADARG;
     if (!coords1 || !coords0 || !delta || !new_coords1 || !flow_cl || B <= 0 || H <= 0 || W <= 0 || delta_ld < 2 || (delta_ld & 1) ||
         flow_ld < 2 || (flow_ld & 1)) return PCFA_E_BADARG;
     if ((int64_t)B * H * W > 0x7fffffffLL) return PCFA_E_TOOLARGE;
-    if ((reinterpret_cast<uintptr_t>(delta) | reinterpret_cast<uintptr_t>(flow_cl)) & 7) return PCFA_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(delta) & (delta_dtype ? 3 : 7)) || (reinterpret_cast<uintptr_t>(flow_cl) & 7)) return PCFA_E_BADARG;
     const int n = B * H * W;
-    flow_step_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords1, coords0, delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
+    if (delta_dtype == 0)
+        flow_step_kernel<float><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((const float*)coords1, coords0, (const float*)delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
+    else
+        flow_step_kernel<__half><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((const float*)coords1, coords0, (const __half*)delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
     return after_launch();
 }

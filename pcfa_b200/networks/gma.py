@@ -64,6 +64,46 @@ class Attention(nn.Module):
         return sim.softmax(dim=-1)
 
 
+class _AttnSource(torch.autograd.Function):
+    """Identity on the attention matrix.  Every iteration's aggregation consumes the returned tensor, returns no gradient
+    for it and instead accumulates its share (g · vᵀ) into one buffer with the GEMM's own beta = 1 epilogue; this node runs
+    after all of them and hands the sum on — instead of autograd adding five 99 MB fp16 gradients (0.28 ms per closure)."""
+
+    @staticmethod
+    def forward(ctx, attn, holder):
+        ctx.holder = holder
+        ctx.set_materialize_grads(False)
+        return attn.view_as(attn)
+
+    @staticmethod
+    def backward(ctx, g):
+        acc = ctx.holder.pop("acc", None)
+        if acc is None:
+            return g, None
+        return (acc.view(ctx.holder["shape"]) if g is None else acc.view(ctx.holder["shape"]) + g), None
+
+
+class _AttnBmm(torch.autograd.Function):
+    """attn · v for one iteration; dL/dv here, dL/dattn accumulated in the shared holder (see _AttnSource)."""
+
+    @staticmethod
+    def forward(ctx, a2, vm, holder):
+        ctx.save_for_backward(a2, vm)
+        ctx.holder = holder
+        return torch.bmm(a2, vm)
+
+    @staticmethod
+    def backward(ctx, g):
+        a2, vm = ctx.saved_tensors
+        gvm = torch.bmm(a2.transpose(1, 2), g) if ctx.needs_input_grad[1] else None
+        acc = ctx.holder.get("acc")
+        if acc is None:
+            ctx.holder["acc"] = torch.bmm(g, vm.transpose(1, 2))
+        else:
+            acc.baddbmm_(g, vm.transpose(1, 2))
+        return None, gvm, None
+
+
 class Aggregate(nn.Module):
     def __init__(self, dim, heads=4, dim_head=128):
         super().__init__()
@@ -81,7 +121,11 @@ class Aggregate(nn.Module):
             # channels-last memory IS 'b (x y) d': the aggregation is one batched GEMM on views, no copies either side
             vm = v.permute(0, 2, 3, 1).reshape(b, h * w, -1)
             a2 = attn.reshape(b, h * w, h * w)
-            out = torch.bmm(a2.to(vm.dtype) if a2.dtype != vm.dtype else a2, vm)
+            holder = getattr(attn, "_pcfa_holder", None)
+            if holder is not None and a2.dtype == vm.dtype and torch.is_grad_enabled():
+                out = _AttnBmm.apply(a2, vm, holder)
+            else:
+                out = torch.bmm(a2.to(vm.dtype) if a2.dtype != vm.dtype else a2, vm)
             out = out.view(b, h, w, -1).permute(0, 3, 1, 2)                         # channels-last [b, d, h, w]
             if self.project is not None:
                 out = self.project(out)
@@ -108,7 +152,9 @@ class GMAUpdateBlock(nn.Module):
         sm_100 kernels are NHWC-only and otherwise convert around each of the ~17 convolutions per iteration.
         step_sources (gru_ops.hoist_sources): the whole SepConvGRU step as one autograd node with the context features'
         share of its convolutions hoisted out of the iteration loop (fp16 kernels under autocast, csrc/gru_half.cu)."""
-        motion = self.encoder(flow, corr)
+        # channels-last: the encoder's last convolution gets two zero filters and the flow written over them (no 126-channel
+        # tensor for cuDNN to pad, no concatenation), as in RAFT's update block
+        motion = self.encoder(flow, corr, bool(getattr(self, "channels_last", False)) and flow.is_cuda)
         motion_global = self.aggregator(attention, motion)
         if step_sources is not None:
             from ..gru_ops import gru_step_x
@@ -161,6 +207,11 @@ class RAFTGMA(nn.Module):
             net, inp = torch.split(self.cnet(image1), [128, 128], dim=1)
             net, inp = torch.tanh(net), torch.relu(inp)
             attention = self.att(inp)
+        if (dev_type == "cuda" and torch.is_grad_enabled() and attention.requires_grad and self.args["num_heads"] == 1
+                and os.environ.get("PCFA_GMA_ATTN_ACC", "1") != "0"):
+            holder = {"shape": tuple(attention.shape)}
+            attention = _AttnSource.apply(attention, holder)
+            attention._pcfa_holder = holder
         N, _, H, W = image1.shape
         coords0 = coords_grid(N, H // 8, W // 8, image1.device)
         coords1 = coords0.clone()
@@ -179,16 +230,27 @@ class RAFTGMA(nn.Module):
                 from ..gru_ops import hoist_sources
                 with torch.autocast(dev_type, enabled=amp):
                     step_sources = hoist_sources(self.update_block.gru.hoisted(inp))
+        flow_cl = None
         for itr in range(iters):
             coords1 = coords1.detach()
             corr = corr_fn(coords1, channels_last=True) if cl else corr_fn(coords1)
-            flow = coords1 - coords0
             need_up = (not test_mode) or itr == iters - 1
-            with torch.autocast(dev_type, enabled=amp):
-                fl = flow.contiguous(memory_format=torch.channels_last) if cl else flow
-                net, up_mask, delta_flow = self.update_block(net, inp, corr, fl, attention, want_mask=need_up, raw_mask=cl,
-                                                             step_sources=step_sources, last=itr == iters - 1)
-            coords1 = coords1 + delta_flow.float().contiguous()
+            if cl:
+                # zero-padded 8-channel flow (a tensor-core 7x7 convolution without cuDNN's channel padding) and ONE launch for
+                # coords1 += delta, flow = coords1 - coords0 (conv_ops.flow_step)
+                from ..conv_ops import flow_step, padded_flow
+                if flow_cl is None:
+                    flow_cl = padded_flow(coords1 - coords0, 8)
+                with torch.autocast(dev_type, enabled=amp):
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow_cl, attention, want_mask=need_up, raw_mask=True,
+                                                                 step_sources=step_sources, last=itr == iters - 1)
+                coords1, flow_cl = flow_step(coords1, coords0, delta_flow, 8)
+            else:
+                flow = coords1 - coords0
+                with torch.autocast(dev_type, enabled=amp):
+                    net, up_mask, delta_flow = self.update_block(net, inp, corr, flow, attention, want_mask=need_up, raw_mask=False,
+                                                                 step_sources=step_sources, last=itr == iters - 1)
+                coords1 = coords1 + delta_flow.float().contiguous()
             if need_up:
                 if cl:                                 # fused kernel on the raw mask (csrc/upsample.cu), fp32 like the reference's
                     from ..upsample import convex_upsample as _fused_upsample      # fp32 softmax under autocast

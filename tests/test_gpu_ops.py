@@ -637,3 +637,7 @@ def test_flow_step_matches_torch_and_passes_the_gradient():
     go = torch.randn(new.shape, generator=g).cuda()
     (new * go).sum().backward()
     assert torch.equal(d8.grad[:, :2], go) and float(d8.grad[:, 2:].abs().max()) == 0.0
+    h8 = d8.detach().half().contiguous(memory_format=torch.channels_last)           # GMA: fp16 flow head
+    newh, flowh = flow_step(c1, c0, h8[:, :2], 8)
+    refh = c1 + h8[:, :2].float()
+    assert torch.equal(newh, refh) and torch.equal(flowh[:, :2], refh - c0) and newh.dtype == torch.float32
