@@ -6,10 +6,10 @@ set -e
 mkdir -p scratch_geo/obj
 build_variant() {   # tag, extra nvcc flags
   for f in pcfa_b200/csrc/*.cu; do
-    nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude $2 \
+    nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude $2 \
          -c "$f" -o "scratch_geo/obj/$(basename "$f" .cu).o"
   done
-  nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -shared -o "scratch_geo/libpcfa_$1.so" scratch_geo/obj/*.o -lcuda
+  nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -shared -o "scratch_geo/libpcfa_$1.so" scratch_geo/obj/*.o
 }
 if [ "$1" = build ]; then
   build_variant g4x32 "-DPCFA_TC_PH=4 -DPCFA_TC_PW=32"     # shipped shape
