@@ -422,9 +422,9 @@ int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int
 int pcfa_relu_mask_backward_rows(const void* y, const void* grad_y, void* grad_x, int64_t rows, int C, int64_t ld, float slope,
                                  int dtype, pcfa_stream_t stream);
 /* out = relu(a + b), element-wise, any dense layout shared by the three tensors: the tail of the encoders' residual blocks
- * (models/raft/extractor.py:55,112) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */
+ * (models/raft/extractor.py:56,116) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */
 int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, int dtype, pcfa_stream_t stream);
-/* Coordinate bookkeeping of one RAFT/GMA refinement iteration in one launch (models/raft/raft.py:123-139):
+/* Coordinate bookkeeping of one RAFT/GMA refinement iteration in one launch (models/raft/raft.py:123-131):
  * new_coords1 = coords1 + delta[..., 0:2], flow_cl = new_coords1 - coords0.  coords*: [B,2,H,W]; delta: channels-last with
  * delta_ld (even) channels per pixel; flow_cl: [B,H,W,flow_ld] = torch.channels_last memory of [B,flow_ld,H,W], channels 2.. are
  * zero-filled (flow_ld = 8 lets the 7x7 convolution on the flow run as a tensor-core implicit GEMM). */

@@ -101,7 +101,7 @@ relu_mask_rows_f16_kernel(const __half* __restrict__ y, const __half* __restrict
     }
 }
 
-// out = relu(a + b): the tail of a residual block (models/raft/extractor.py:55) in one pass instead of add + clamp
+// out = relu(a + b): the tail of a residual block (models/raft/extractor.py:56) in one pass instead of add + clamp
 __global__ void __launch_bounds__(BA_THREADS)
 add_relu_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n4) {
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
@@ -124,7 +124,7 @@ add_relu_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, 
     }
 }
 
-// One launch for the coordinate bookkeeping of a RAFT/GMA iteration (models/raft/raft.py:123-139): coords1 += delta_flow,
+// One launch for the coordinate bookkeeping of a RAFT/GMA iteration (models/raft/raft.py:123-131): coords1 += delta_flow,
 // flow = coords1 - coords0.  coords: [B,2,H,W]; delta: channels-last with `ld` channels per pixel (the flow head's padded
 // output), channels 0..1 used; flow_cl: [B,H,W,2] (channels-last of [B,2,H,W]) for the next iteration's motion encoder.
 template <typename TD>
