@@ -65,9 +65,10 @@ class Attention(nn.Module):
 
 
 class _AttnSource(torch.autograd.Function):
-    """Identity on the attention matrix.  Every iteration's aggregation consumes the returned tensor, returns no gradient
-    for it and instead accumulates its share (g · vᵀ) into one buffer with the GEMM's own beta = 1 epilogue; this node runs
-    after all of them and hands the sum on — instead of autograd adding five 99 MB fp16 gradients (0.28 ms per closure)."""
+    """Identity on the attention matrix.  Every iteration's aggregation consumes the returned tensor and returns no gradient
+    for it; it only files its (g_k, v_k) pair in the shared holder.  This node runs after all of them and computes
+    dL/dattn = sum_k g_k v_k^T as ONE GEMM with K = iterations x 128 — instead of six K = 128 GEMMs that each write a 99 MB
+    fp16 matrix plus five adds of those matrices (0.45 ms -> 0.1 ms per closure)."""
 
     @staticmethod
     def forward(ctx, attn, holder):
@@ -77,14 +78,17 @@ class _AttnSource(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        acc = ctx.holder.pop("acc", None)
-        if acc is None:
+        gs, vs = ctx.holder.pop("g", None), ctx.holder.pop("v", None)
+        if not gs:
             return g, None
-        return (acc.view(ctx.holder["shape"]) if g is None else acc.view(ctx.holder["shape"]) + g), None
+        G = gs[0] if len(gs) == 1 else torch.cat(gs, dim=2)             # [b, n, K]
+        V = vs[0] if len(vs) == 1 else torch.cat(vs, dim=2)
+        acc = torch.bmm(G, V.transpose(1, 2)).view(ctx.holder["shape"])
+        return (acc if g is None else acc + g), None
 
 
 class _AttnBmm(torch.autograd.Function):
-    """attn · v for one iteration; dL/dv here, dL/dattn accumulated in the shared holder (see _AttnSource)."""
+    """attn · v for one iteration; dL/dv here, the dL/dattn share deferred to _AttnSource."""
 
     @staticmethod
     def forward(ctx, a2, vm, holder):
@@ -96,11 +100,8 @@ class _AttnBmm(torch.autograd.Function):
     def backward(ctx, g):
         a2, vm = ctx.saved_tensors
         gvm = torch.bmm(a2.transpose(1, 2), g) if ctx.needs_input_grad[1] else None
-        acc = ctx.holder.get("acc")
-        if acc is None:
-            ctx.holder["acc"] = torch.bmm(g, vm.transpose(1, 2))
-        else:
-            acc.baddbmm_(g, vm.transpose(1, 2))
+        ctx.holder.setdefault("g", []).append(g)
+        ctx.holder.setdefault("v", []).append(vm)
         return None, gvm, None
 
 
