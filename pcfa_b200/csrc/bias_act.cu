@@ -101,6 +101,20 @@ relu_mask_rows_f16_kernel(const __half* __restrict__ y, const __half* __restrict
     }
 }
 
+// dst[r][c] += src[r * ld + c]: a dense gradient plus a channel slice of a wider channels-last gradient (the skip branch of a
+// DenseNet-style concatenation) in one vectorised pass — ATen adds a strided operand with its non-vectorised kernel
+__global__ void __launch_bounds__(BA_THREADS)
+add_rows_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4, int c4, int64_t ld) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
+        const int64_t r = v / c4;
+        const int c = (int)(v - r * c4);
+        float4 d = reinterpret_cast<float4*>(dst)[v];
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + r * ld) + c);
+        d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
+        reinterpret_cast<float4*>(dst)[v] = d;
+    }
+}
+
 // out = relu(a + b): the tail of a residual block (models/raft/extractor.py:56) in one pass instead of add + clamp
 __global__ void __launch_bounds__(BA_THREADS)
 add_relu_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n4) {
@@ -223,5 +237,13 @@ extern "C" int pcfa_flow_step(const float* coords1, const float* coords0, const 
         flow_step_kernel<float><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((const float*)coords1, coords0, (const float*)delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
     else
         flow_step_kernel<__half><<<(n + 255) / 256, 256, 0, as_stream(stream)>>>((const float*)coords1, coords0, (const __half*)delta, delta_ld, new_coords1, flow_cl, flow_ld, B, H * W);
+    return after_launch();
+}
+
+extern "C" int pcfa_add_rows_inplace(float* dst, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream) {
+    if (!dst || !src || rows <= 0 || C <= 0 || ld < C || C % 4 || ld % 4 ||
+        ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15)) return PCFA_E_BADARG;
+    const int64_t nv = rows * (C / 4);
+    add_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>(dst, src, nv, C / 4, ld);
     return after_launch();
 }

@@ -106,7 +106,12 @@ class PWCDCNet(nn.Module):
 
     def _decode(self, lvl, x):
         for i in range(5):
-            x = self._cat((getattr(self, f"conv{lvl}_{i}")(x), x))
+            m = getattr(self, f"conv{lvl}_{i}")
+            if self._cl(x) and len(m) == 2:             # conv + LeakyReLU + concatenation as one autograd node (conv_ops)
+                from ..conv_ops import dense_conv_cat
+                x = dense_conv_cat(m[0], x, float(m[1].negative_slope))
+            else:
+                x = self._cat((m(x), x))
         return x, self._plain(getattr(self, f"predict_flow{lvl}"), x)
 
     def forward(self, im1, im2):

@@ -641,3 +641,26 @@ def test_flow_step_matches_torch_and_passes_the_gradient():
     newh, flowh = flow_step(c1, c0, h8[:, :2], 8)
     refh = c1 + h8[:, :2].float()
     assert torch.equal(newh, refh) and torch.equal(flowh[:, :2], refh - c0) and newh.dtype == torch.float32
+
+
+def test_dense_conv_cat_matches_torch():
+    """x -> cat(LeakyReLU(conv(x)), x) as one node (PWCNet's DenseNet decoder) against the torch composition, incl. the
+    zero-padded input channels of the decoder's first concatenation."""
+    from pcfa_b200.conv_ops import dense_conv_cat
+    g = torch.Generator().manual_seed(4)
+    for cin, cpad, cout in ((88, 88, 128), (81, 88, 128), (216, 216, 96)):
+        conv = torch.nn.Conv2d(cin, cout, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+        for p in conv.parameters():
+            p.requires_grad = False
+        x = torch.randn(1, cpad, 12, 20, generator=g).cuda()
+        x[:, cin:] = 0
+        x = x.contiguous(memory_format=torch.channels_last)
+        a, b = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        out = dense_conv_cat(conv, a, 0.1)
+        ref = torch.cat((torch.nn.functional.leaky_relu(conv(b[:, :cin]), 0.1), b), 1)
+        assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+        assert_close(npy(out), npy(ref), what="dense_conv_cat fwd", **TOL)
+        go = torch.randn(ref.shape, generator=g).cuda()
+        (out * go).sum().backward()
+        (ref * go).sum().backward()
+        assert_close(npy(a.grad[:, :cin]), npy(b.grad[:, :cin]), what="dense_conv_cat grad", **TOL)
