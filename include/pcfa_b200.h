@@ -422,7 +422,7 @@ int pcfa_relu_mask_backward(const void* y, const void* grad_y, void* grad_x, int
 int pcfa_relu_mask_backward_rows(const void* y, const void* grad_y, void* grad_x, int64_t rows, int C, int64_t ld, float slope,
                                  int dtype, pcfa_stream_t stream);
 /* dst[r][c] += src[r*ld + c] (fp32): a dense [rows][C] gradient plus a channel slice of a wider channels-last gradient — the
- * skip branch of x = cat(conv(x), x) (models/PWCNet/PWCNet.py:226-230 and the four levels below it).  C % 4 == 0, ld % 4 == 0. */
+ * skip branch of x = cat(conv(x), x) (models/PWCNet/PWCNet.py:253-257 and the four levels below it).  C % 4 == 0, ld % 4 == 0. */
 int pcfa_add_rows_inplace(float* dst, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream);
 /* out = relu(a + b), element-wise, any dense layout shared by the three tensors: the tail of the encoders' residual blocks
  * (models/raft/extractor.py:56,116) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */

@@ -185,7 +185,7 @@ class _ConvBiasAct(Function):
 
 class _DenseConvCat(Function):
     """x -> cat(act(conv(x) + b), x) along the channels (channels-last, stride-1 convolution with frozen weights) as ONE
-    autograd node: PWCNet's DenseNet decoder (PWCNet.py:226-230).  Backward: the activation mask reads its gradient straight
+    autograd node: PWCNet's DenseNet decoder (PWCNet.py:253-257).  Backward: the activation mask reads its gradient straight
     from the first channels of the concatenation's gradient, cuDNN's data gradient follows, and the skip branch's share — the
     remaining channels, a strided slice — is added in place by one vectorised kernel.  autograd otherwise sums a strided and a
     dense tensor with ATen's non-vectorised add (51 launches, 0.34 ms of a 4.0 ms PWCNet closure)."""
