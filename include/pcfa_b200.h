@@ -424,6 +424,9 @@ int pcfa_relu_mask_backward_rows(const void* y, const void* grad_y, void* grad_x
 /* dst[r][c] += src[r*ld + c] (fp32): a dense [rows][C] gradient plus a channel slice of a wider channels-last gradient — the
  * skip branch of x = cat(conv(x), x) (models/PWCNet/PWCNet.py:253-257 and the four levels below it).  C % 4 == 0, ld % 4 == 0. */
 int pcfa_add_rows_inplace(float* dst, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream);
+/* out = a + src-slice, out-of-place: where a tensor feeds a convolution AND a later concatenation (the encoder skips of
+ * models/FlowNet/FlowNetS.py:63-88, FlowNetC.py:106-121, FlowNetSD.py:69-99, FlowNetFusion.py:50-65). */
+int pcfa_add_rows(float* out, const float* a, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream);
 /* out = relu(a + b), element-wise, any dense layout shared by the three tensors: the tail of the encoders' residual blocks
  * (models/raft/extractor.py:56,116) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */
 int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, int dtype, pcfa_stream_t stream);

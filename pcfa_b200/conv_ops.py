@@ -183,6 +183,38 @@ class _ConvBiasAct(Function):
         return gin, None, None, None, None, None, None, None, None, None, None
 
 
+class _Fork(Function):
+    """x -> (x, x) for a tensor with two consumers, one of which is a channels-last concatenation: the backward receives the
+    two gradients SEPARATELY (autograd would sum a dense tensor and a strided channel slice with ATen's non-vectorised add)
+    and adds them with one vectorised kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None or g2 is None:
+            return g2 if g1 is None else g1
+        for a, b in ((g1, g2), (g2, g1)):
+            if a.dtype == torch.float32 and _is_cl(a) and a.shape[1] % 4 == 0:
+                ld = _channel_slice_ld(b, a)
+                if ld and ld % 4 == 0 and b.data_ptr() % 16 == 0:
+                    out = torch.empty_like(a)
+                    _lib.check(_lib.load().pcfa_add_rows(_lib.ptr(out), _lib.ptr(a), _lib.ptr(b), a.numel() // a.shape[1], a.shape[1], ld,
+                                                         _lib.stream()), "pcfa_add_rows")
+                    return out
+        return g1 + g2
+
+
+def fork(x: torch.Tensor):
+    """(x, x) — give one to the next convolution and the other to the concatenation that follows later (see _Fork)."""
+    if _ENABLED and x.is_cuda and x.requires_grad and x.dtype == torch.float32 and x.dim() == 4 and os.environ.get("PCFA_FORK", "1") != "0":
+        return _Fork.apply(x)
+    return x, x
+
+
 class _DenseConvCat(Function):
     """x -> cat(act(conv(x) + b), x) along the channels (channels-last, stride-1 convolution with frozen weights) as ONE
     autograd node: PWCNet's DenseNet decoder (PWCNet.py:253-257).  Backward: the activation mask reads its gradient straight

@@ -104,11 +104,11 @@ relu_mask_rows_f16_kernel(const __half* __restrict__ y, const __half* __restrict
 // dst[r][c] += src[r * ld + c]: a dense gradient plus a channel slice of a wider channels-last gradient (the skip branch of a
 // DenseNet-style concatenation) in one vectorised pass — ATen adds a strided operand with its non-vectorised kernel
 __global__ void __launch_bounds__(BA_THREADS)
-add_rows_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4, int c4, int64_t ld) {
+add_rows_f32_kernel(float* dst, const float* a, const float* __restrict__ src, int64_t n4, int c4, int64_t ld) {      // dst may be a
     for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
         const int64_t r = v / c4;
         const int c = (int)(v - r * c4);
-        float4 d = reinterpret_cast<float4*>(dst)[v];
+        float4 d = reinterpret_cast<const float4*>(a)[v];
         const float4 a = __ldg(reinterpret_cast<const float4*>(src + r * ld) + c);
         d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
         reinterpret_cast<float4*>(dst)[v] = d;
@@ -244,6 +244,16 @@ extern "C" int pcfa_add_rows_inplace(float* dst, const float* src, int64_t rows,
     if (!dst || !src || rows <= 0 || C <= 0 || ld < C || C % 4 || ld % 4 ||
         ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15)) return PCFA_E_BADARG;
     const int64_t nv = rows * (C / 4);
-    add_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>(dst, src, nv, C / 4, ld);
+    add_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>(dst, dst, src, nv, C / 4, ld);
+    return after_launch();
+}
+
+// out[r][c] = a[r][c] + src[r*ld + c]  (out and a dense [rows][C]): the sum of a dense gradient and a channel slice of a wider
+// channels-last gradient where a tensor feeds both a convolution and a later concatenation (FlowNet's encoder skips)
+extern "C" int pcfa_add_rows(float* out, const float* a, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream) {
+    if (!out || !a || !src || rows <= 0 || C <= 0 || ld < C || C % 4 || ld % 4 ||
+        ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(src)) & 15)) return PCFA_E_BADARG;
+    const int64_t nv = rows * (C / 4);
+    add_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>(out, a, src, nv, C / 4, ld);
     return after_launch();
 }

@@ -50,6 +50,12 @@ def _cat(xs):
     return torch.cat(tuple(xs), 1)
 
 
+def _skip(x):
+    """(for the next encoder convolution, for the decoder's concatenation): conv_ops.fork on the GPU path."""
+    from ..conv_ops import fork
+    return fork(x) if _PAD else (x, x)
+
+
 def _pf(m, x):
     """predict_flow / up-sampling (de)convolutions on a possibly zero-padded input."""
     from ..conv_ops import apply_conv
@@ -103,15 +109,15 @@ class FlowNetC(_Refinement):
         self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
 
     def forward(self, x):
-        a2 = self.conv2(self.conv1(x[:, 0:3]))
+        a2, a2s = _skip(self.conv2(self.conv1(x[:, 0:3])))
         a3 = self.conv3(a2)
         b3 = self.conv3(self.conv2(self.conv1(x[:, 3:])))
         corr = self.corr_activation(self.corr(a3, b3))
-        c3 = self.conv3_1(_cat((self.conv_redir(a3), corr)))
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        c3, c3s = _skip(self.conv3_1(_cat((self.conv_redir(a3), corr))))
+        c4, c4s = _skip(self.conv4_1(self.conv4(c3)))
+        c5, c5s = _skip(self.conv5_1(self.conv5(c4)))
         c6 = self.conv6_1(self.conv6(c5))
-        return self._decode(c6, c5, c4, c3, a2)
+        return self._decode(c6, c5s, c4s, c3s, a2s)
 
 
 class FlowNetS(_Refinement):
@@ -127,12 +133,12 @@ class FlowNetS(_Refinement):
         self.upsample1 = nn.Upsample(scale_factor=4, mode='bilinear')
 
     def forward(self, x):
-        c2 = self.conv2(self.conv1(x))
-        c3 = self.conv3_1(self.conv3(c2))
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        c2, c2s = _skip(self.conv2(self.conv1(x)))
+        c3, c3s = _skip(self.conv3_1(self.conv3(c2)))
+        c4, c4s = _skip(self.conv4_1(self.conv4(c3)))
+        c5, c5s = _skip(self.conv5_1(self.conv5(c4)))
         c6 = self.conv6_1(self.conv6(c5))
-        return self._decode(c6, c5, c4, c3, c2)
+        return self._decode(c6, c5s, c4s, c3s, c2s)
 
 
 class FlowNetSD(nn.Module):
@@ -157,19 +163,19 @@ class FlowNetSD(nn.Module):
 
     def forward(self, x):
         c1 = self.conv1_1(self.conv1(self.conv0(x)))
-        c2 = self.conv2_1(self.conv2(c1))
-        c3 = self.conv3_1(self.conv3(c2))
-        c4 = self.conv4_1(self.conv4(c3))
-        c5 = self.conv5_1(self.conv5(c4))
+        c2, c2s = _skip(self.conv2_1(self.conv2(c1)))
+        c3, c3s = _skip(self.conv3_1(self.conv3(c2)))
+        c4, c4s = _skip(self.conv4_1(self.conv4(c3)))
+        c5, c5s = _skip(self.conv5_1(self.conv5(c4)))
         c6 = self.conv6_1(self.conv6(c5))
         flow6 = _pf(self.predict_flow6, c6)
-        cat5 = _cat((c5, self.deconv5(c6), _pf(self.upsampled_flow6_to_5, flow6)))
+        cat5 = _cat((c5s, self.deconv5(c6), _pf(self.upsampled_flow6_to_5, flow6)))
         flow5 = _pf(self.predict_flow5, self.inter_conv5(cat5))
-        cat4 = _cat((c4, self.deconv4(cat5), _pf(self.upsampled_flow5_to_4, flow5)))
+        cat4 = _cat((c4s, self.deconv4(cat5), _pf(self.upsampled_flow5_to_4, flow5)))
         flow4 = _pf(self.predict_flow4, self.inter_conv4(cat4))
-        cat3 = _cat((c3, self.deconv3(cat4), _pf(self.upsampled_flow4_to_3, flow4)))
+        cat3 = _cat((c3s, self.deconv3(cat4), _pf(self.upsampled_flow4_to_3, flow4)))
         flow3 = _pf(self.predict_flow3, self.inter_conv3(cat3))
-        cat2 = _cat((c2, self.deconv2(cat3), _pf(self.upsampled_flow3_to_2, flow3)))
+        cat2 = _cat((c2s, self.deconv2(cat3), _pf(self.upsampled_flow3_to_2, flow3)))
         flow2 = _pf(self.predict_flow2, self.inter_conv2(cat2))
         return (flow2, flow3, flow4, flow5, flow6) if self.training else (flow2,)
 
@@ -188,13 +194,13 @@ class FlowNetFusion(nn.Module):
         _xavier(self)
 
     def forward(self, x):
-        c0 = self.conv0(x)
-        c1 = self.conv1_1(self.conv1(c0))
+        c0, c0s = _skip(self.conv0(x))
+        c1, c1s = _skip(self.conv1_1(self.conv1(c0)))
         c2 = self.conv2_1(self.conv2(c1))
         flow2 = _pf(self.predict_flow2, c2)
-        cat1 = _cat((c1, self.deconv1(c2), _pf(self.upsampled_flow2_to_1, flow2)))
+        cat1 = _cat((c1s, self.deconv1(c2), _pf(self.upsampled_flow2_to_1, flow2)))
         flow1 = _pf(self.predict_flow1, self.inter_conv1(cat1))
-        cat0 = _cat((c0, self.deconv0(cat1), _pf(self.upsampled_flow1_to_0, flow1)))
+        cat0 = _cat((c0s, self.deconv0(cat1), _pf(self.upsampled_flow1_to_0, flow1)))
         return _pf(self.predict_flow0, self.inter_conv0(cat0))
 
 

@@ -664,3 +664,23 @@ def test_dense_conv_cat_matches_torch():
         (out * go).sum().backward()
         (ref * go).sum().backward()
         assert_close(npy(a.grad[:, :cin]), npy(b.grad[:, :cin]), what="dense_conv_cat grad", **TOL)
+
+
+def test_fork_joins_dense_and_sliced_gradients():
+    """conv_ops.fork: a tensor feeding a convolution and a later channels-last concatenation gets ONE vectorised gradient join."""
+    from pcfa_b200.conv_ops import fork
+    from pcfa_b200.gru_ops import cat_channels
+    g = torch.Generator().manual_seed(8)
+    conv = torch.nn.Conv2d(64, 32, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(1, 64, 12, 20, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    other = torch.randn(1, 30, 12, 20, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    grads = []
+    for use_fork in (True, False):
+        a = x.clone().requires_grad_(True)
+        t = a * 1.0                                               # non-leaf, like an encoder feature
+        t1, t2 = fork(t) if use_fork else (t, t)
+        out = cat_channels([t2, conv(t1), other], True, pad_to=8)
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).cuda().contiguous(memory_format=torch.channels_last)
+        (out * w).sum().backward()
+        grads.append(a.grad.clone())
+    assert_close(npy(grads[0]), npy(grads[1]), what="fork grad", **TIGHT)
