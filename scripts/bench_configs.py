@@ -46,11 +46,13 @@ for name in only:
                 ua.run_batch(i1, i2, steps)
                 torch.cuda.synchronize()
                 return time.perf_counter() - t0, ua.closure_evals - n0
-            run(4)
-            t1, n1 = min((run(1) for _ in range(2)), key=lambda r: r[0])
-            t4, n4 = min((run(4) for _ in range(2)), key=lambda r: r[0])
-            row.update(outer_step_s=(t4 - t1) / 3, closures_per_outer_step=(n4 - n1) / 3,
-                       ms_per_closure_incl_host=1e3 * (t4 - t1) / max(1, n4 - n1), pairs=8)
+            # every run_batch call rebuilds the objective and re-captures the closure graph (~1 s): difference a long and a
+            # short run so that this set-up cancels (with 4 vs 1 steps its jitter could exceed the three steps' time)
+            run(2)
+            t1, n1 = min((run(1) for _ in range(3)), key=lambda r: r[0])
+            t9, n9 = min((run(9) for _ in range(2)), key=lambda r: r[0])
+            row.update(outer_step_s=(t9 - t1) / 8, closures_per_outer_step=(n9 - n1) / 8,
+                       ms_per_closure_incl_host=1e3 * (t9 - t1) / max(1, n9 - n1), pairs=8)
         elif name.endswith("batch8"):
             # BASELINE config 3 at N = 1: the eight Sintel-shaped pairs of the batch evaluated as ONE batched joint closure
             # (per-pair delta, clipping); closure time only
