@@ -65,6 +65,16 @@ def test_layout_and_size_helpers_match_reference_arithmetic():
     assert lib.pcfa_fn2corr_output_size(48, 160, 20, 1, 20, 1, 2, C.byref(oc), C.byref(oh), C.byref(ow)) == 0
     assert (oc.value, oh.value, ow.value) == (441, 48, 160)      # FlowNetC.py:26-31
     assert lib.pcfa_fn2corr_output_size(48, 160, 3, 1, 20, 1, 2, C.byref(oc), C.byref(oh), C.byref(ow)) == -1
+    # occupancy bitmap of the sparse backward: one row per 32 queries, one bit per 32-cell chunk of every level
+    chunks = sum(-(-(h * w) // 32) for h, w in zip(hs, ws))                 # 220 + 54 + 13 + 3
+    assert chunks == 290
+    assert lib.pcfa_corr_occupancy_bytes(1, 55, 128, 4) == 220 * (-(-chunks // 32)) * 4 == 8800
+    assert lib.pcfa_corr_occupancy_bytes(8, 55, 128, 4) == 8 * 8800
+    assert lib.pcfa_corr_occupancy_bytes(0, 55, 128, 4) == 0
+    # argument errors of the occupancy / glue entry points (validated before any launch)
+    assert lib.pcfa_corr_occupancy_mark(None, 1, None, 1, 55, 128, 4, 4, None) == -1
+    assert lib.pcfa_add_rows_inplace(None, None, 1, 4, 4, None) == -1
+    assert lib.pcfa_flow_step(None, None, None, 8, 0, None, None, 8, 1, 55, 128, None) == -1
 
 
 def test_no_cpu_fallback_on_cpu_tensors():
