@@ -427,6 +427,9 @@ int pcfa_add_rows_inplace(float* dst, const float* src, int64_t rows, int C, int
 /* out = a + src-slice, out-of-place: where a tensor feeds a convolution AND a later concatenation (the encoder skips of
  * models/FlowNet/FlowNetS.py:63-88, FlowNetC.py:106-121, FlowNetSD.py:69-99, FlowNetFusion.py:50-65). */
 int pcfa_add_rows(float* out, const float* a, const float* src, int64_t rows, int C, int64_t ld, pcfa_stream_t stream);
+/* grad_x = y > 0 ? g1 + g2 : 0 (fp32, any dense layout shared by the four tensors): the ReLU mask of a residual tail applied
+ * to the sum of the gradients of its two consumers (next block's convolution and skip branch) in one pass. */
+int pcfa_relu_mask2_backward(const float* y, const float* g1, const float* g2, float* grad_x, int64_t n, pcfa_stream_t stream);
 /* out = relu(a + b), element-wise, any dense layout shared by the three tensors: the tail of the encoders' residual blocks
  * (models/raft/extractor.py:56,116) in one pass.  dtype 0 = fp32 (n % 4 == 0), 1 = fp16 (n % 8 == 0). */
 int pcfa_add_relu_forward(const void* a, const void* b, void* out, int64_t n, int dtype, pcfa_stream_t stream);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "pcfa_relu_mask_backward_rows": (c_i, [c_fp, c_fp, c_fp, c_i64, c_i, c_i64, c_f, c_i, c_fp]),
     "pcfa_add_rows_inplace": (c_i, [c_fp, c_fp, c_i64, c_i, c_i64, c_fp]),
     "pcfa_add_rows": (c_i, [c_fp, c_fp, c_fp, c_i64, c_i, c_i64, c_fp]),
+    "pcfa_relu_mask2_backward": (c_i, [c_fp, c_fp, c_fp, c_fp, c_i64, c_fp]),
     "pcfa_add_relu_forward": (c_i, [c_fp, c_fp, c_fp, c_i64, c_i, c_fp]),
     "pcfa_flow_step": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_fp, c_fp, c_i, c_i, c_i, c_i, c_fp]),
     "pcfa_cat2_channels_last_h": (c_i, [c_fp, c_fp, c_fp, c_i, c_i, c_i64, c_fp]),

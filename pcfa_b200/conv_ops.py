@@ -66,11 +66,51 @@ class _AddReLU(Function):
         return gx, gx
 
 
-def add_relu(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """relu(a + b); one kernel when both are CUDA tensors of the same dense layout (fp32 / fp16), torch ops otherwise."""
+class _AddReLUTwin(Function):
+    """relu(a + b) returned TWICE (two views of one tensor) for a residual tail whose result feeds both the next block's
+    convolution and its skip branch: the backward receives the two consumers' gradients separately and applies the ReLU mask
+    to their sum in one pass (autograd would first add them: one more read-read-write pass over up to 58 MB)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        out = torch.empty_like(a)
+        _lib.check(lib.pcfa_add_relu_forward(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.numel(), 0, _lib.stream()), "pcfa_add_relu_forward")
+        ctx.save_for_backward(out)
+        ctx.set_materialize_grads(False)
+        return out, out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        lib = _lib.load()
+        (out,) = ctx.saved_tensors
+        if g1 is None and g2 is None:
+            return None, None
+        fmt = dict(memory_format=_CL) if _is_cl(out) else {}
+        gx = torch.empty_like(out)
+        if g1 is None or g2 is None:
+            g = (g2 if g1 is None else g1).contiguous(**fmt)
+            _lib.check(lib.pcfa_relu_mask_backward(_lib.ptr(out), _lib.ptr(g), _lib.ptr(gx), out.numel(), 0.0, 0, _lib.stream()),
+                       "pcfa_relu_mask_backward")
+        else:
+            g1, g2 = g1.contiguous(**fmt), g2.contiguous(**fmt)
+            _lib.check(lib.pcfa_relu_mask2_backward(_lib.ptr(out), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(gx), out.numel(), _lib.stream()),
+                       "pcfa_relu_mask2_backward")
+        return gx, gx
+
+
+def add_relu(a: torch.Tensor, b: torch.Tensor, twin: bool = False) -> torch.Tensor:
+    """relu(a + b); one kernel when both are CUDA tensors of the same dense layout (fp32 / fp16), torch ops otherwise.
+    twin=True (fp32): the result carries a second autograd handle of itself in `._pcfa_twin`; a consumer that uses the value
+    twice (a residual block: convolution + skip) takes one handle each, see _AddReLUTwin."""
     if (_ENABLED and a.is_cuda and a.shape == b.shape and a.dtype == b.dtype and a.dtype in (torch.float32, torch.float16)
             and a.stride() == b.stride() and (a.is_contiguous() or _is_cl(a)) and a.numel() % 8 == 0
             and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        if twin and a.dtype == torch.float32 and torch.is_grad_enabled() and (a.requires_grad or b.requires_grad) \
+                and os.environ.get("PCFA_ADD_RELU_TWIN", "1") != "0":
+            out, out2 = _AddReLUTwin.apply(a, b)
+            out._pcfa_twin = out2
+            return out
         return _AddReLU.apply(a, b)
     return torch.relu(a + b)
 

@@ -73,6 +73,18 @@ relu_mask_f16_kernel(const __half* __restrict__ y, const __half* __restrict__ gy
     }
 }
 
+// grad_x = y > 0 ? g1 + g2 : 0 — ReLU mask applied to the SUM of two gradients (a residual tail whose output feeds the next
+// block's convolution and its skip branch): one pass instead of autograd's add followed by the mask
+__global__ void __launch_bounds__(BA_THREADS)
+relu_mask2_f32_kernel(const float* __restrict__ y, const float* __restrict__ g1, const float* __restrict__ g2, float* __restrict__ gx, int64_t n4) {
+    for (int64_t v = (int64_t)blockIdx.x * BA_THREADS + threadIdx.x; v < n4; v += (int64_t)gridDim.x * BA_THREADS) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(y) + v), p = __ldg(reinterpret_cast<const float4*>(g1) + v),
+                     q = __ldg(reinterpret_cast<const float4*>(g2) + v);
+        reinterpret_cast<float4*>(gx)[v] = make_float4(a.x > 0.f ? p.x + q.x : 0.f, a.y > 0.f ? p.y + q.y : 0.f,
+                                                       a.z > 0.f ? p.z + q.z : 0.f, a.w > 0.f ? p.w + q.w : 0.f);
+    }
+}
+
 // grad_y is a channel slice of a wider channels-last tensor (the gradient of a concatenation): rows of C elements, ld apart
 __global__ void __launch_bounds__(BA_THREADS)
 relu_mask_rows_f32_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, int64_t n4, int c4, int64_t ld,
@@ -255,5 +267,13 @@ extern "C" int pcfa_add_rows(float* out, const float* a, const float* src, int64
         ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(src)) & 15)) return PCFA_E_BADARG;
     const int64_t nv = rows * (C / 4);
     add_rows_f32_kernel<<<ba_grid(nv), BA_THREADS, 0, as_stream(stream)>>>(out, a, src, nv, C / 4, ld);
+    return after_launch();
+}
+
+extern "C" int pcfa_relu_mask2_backward(const float* y, const float* g1, const float* g2, float* grad_x, int64_t n, pcfa_stream_t stream) {
+    if (!y || !g1 || !g2 || !grad_x || n <= 0 || n % 4 ||
+        ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(grad_x)) & 15))
+        return PCFA_E_BADARG;
+    relu_mask2_f32_kernel<<<ba_grid(n / 4), BA_THREADS, 0, as_stream(stream)>>>(y, g1, g2, grad_x, n / 4);
     return after_launch();
 }

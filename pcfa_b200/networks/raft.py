@@ -104,12 +104,16 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride), self.norm3)
 
     def forward(self, x):
+        # the previous block's tail hands over two autograd handles of its result (conv_ops._AddReLUTwin): one for the
+        # convolution path, one for the skip branch, so that their gradients meet inside that tail's ReLU mask
+        skip = getattr(x, "_pcfa_twin", None)
+        skip = x if skip is None else skip
         y = _conv_norm_act(self.conv1, self.norm1, x, True)
         y = _conv_norm_act(self.conv2, self.norm2, y, True)
         if self.downsample is not None:
-            x = _conv_norm_act(self.downsample[0], self.downsample[1], x, False)
-        from ..conv_ops import add_relu                     # relu(x + y) in one launch on the GPU
-        return add_relu(x, y)
+            skip = _conv_norm_act(self.downsample[0], self.downsample[1], skip, False)
+        from ..conv_ops import add_relu                     # relu(skip + y) in one launch on the GPU
+        return add_relu(skip, y, twin=True)
 
 
 class BottleneckBlock(nn.Module):

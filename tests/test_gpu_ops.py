@@ -684,3 +684,25 @@ def test_fork_joins_dense_and_sliced_gradients():
         (out * w).sum().backward()
         grads.append(a.grad.clone())
     assert_close(npy(grads[0]), npy(grads[1]), what="fork grad", **TIGHT)
+
+
+def test_add_relu_twin_masks_the_sum_of_both_consumers_gradients():
+    from pcfa_b200.conv_ops import add_relu
+    g = torch.Generator().manual_seed(6)
+    conv = torch.nn.Conv2d(64, 64, 3, padding=1).cuda().to(memory_format=torch.channels_last)
+    a = torch.randn(2, 64, 22, 32, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(2, 64, 22, 32, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    res = []
+    for twin in (True, False):
+        a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        out = add_relu(a1, b1, twin=twin)
+        assert (getattr(out, "_pcfa_twin", None) is not None) == twin
+        skip = out._pcfa_twin if twin else out
+        z = add_relu(skip, conv(out))                              # the next block: convolution path + skip branch
+        (z * z).sum().backward()
+        res.append((out.detach().clone(), a1.grad.clone(), b1.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert_close(npy(res[0][1]), npy(res[1][1]), what="twin grad a", **TIGHT)
+    assert_close(npy(res[0][2]), npy(res[1][2]), what="twin grad b", **TIGHT)
+    only = add_relu(a.clone().requires_grad_(True), b, twin=True)    # second handle unused: plain mask
+    only.sum().backward()
