@@ -1,6 +1,6 @@
-"""Sparse backward of the correlation pyramid (pcfa_corr_lookup_backward_cl_occ + pcfa_corr_pyramid_backward_occ): the
-occupancy bitmap is a superset of the non-zero 32x32 blocks of the gradient pyramid, the marked lookup writes the same
-gradient as the plain one, and the block-skipping build backward returns what the dense one returns on the same input."""
+"""Sparse backward of the correlation pyramid (pcfa_corr_occupancy_mark + pcfa_corr_pyramid_backward_occ): the occupancy
+bitmap marked from the lookups' coordinates is a superset of the non-zero 32x32 blocks of the gradient pyramid for every
+lookup kernel and radius, and the block-skipping build backward returns what the dense one returns on the same input."""
 import os
 import subprocess
 import sys
